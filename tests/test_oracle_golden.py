@@ -1,0 +1,68 @@
+"""CPU: the NumPy restatement (oracle/) against the golden vectors the unmodified reference produced."""
+import numpy as np
+import pytest
+
+from oracle.apvast_oracle import ApvastOracle, jdiag, toeplitz_rows
+from tests._golden import compare_state, replay
+
+SMALL = ["tiny", "tiny_hop", "tiny_runA", "tiny_full", "mid"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_golden(name):
+    eng, g, res = replay(ApvastOracle, name)
+    assert res, "no compared blocks"
+    for t, e in res.items():
+        for k, v in e.items():
+            tol = 1e-8 if k.startswith("w_") or k.startswith("out_") else 1e-10
+            assert v <= tol, (name, t, k, v)
+    for a, v in compare_state(eng, g).items():
+        assert v <= 1e-9, (name, a, v)
+
+
+def test_oracle_matches_reference_golden_perceptual_injected():
+    # gain model injected at the libdetectability boundary in both (parity otherwise unpinned)
+    eng, g, res = replay(ApvastOracle, "tiny_perc")
+    for t, e in res.items():
+        for k, v in e.items():
+            assert v <= 1e-8, (t, k, v)
+    st = compare_state(eng, g)
+    assert st["weighting_spectra_A"] <= 1e-12 and st["weighting_spectra_B"] <= 1e-12
+
+
+def test_oracle_matches_reference_golden_cfg1():
+    eng, g, res = replay(ApvastOracle, "cfg1")
+    assert sorted(res) == [1, 5, 9]
+    for t, e in res.items():
+        for k, v in e.items():
+            tol = 1e-8 if k.startswith("w_") or k.startswith("out_") else 1e-10
+            assert v <= tol, (t, k, v)
+
+
+def test_toeplitz_quirk_matches_scipy():
+    import scipy.linalg as sla
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(40)
+    J = 7
+    want = sla.toeplitz(np.flipud(s[0:J]), s[J:])      # exactly the reference expression (apvast.py:336-338)
+    assert np.array_equal(toeplitz_rows(s, J), want)
+
+
+def test_jdiag_identities():
+    # jdiag.m:33-35: U'AU = D, U'BU = I
+    rng = np.random.default_rng(3)
+    n = 40
+    X = rng.standard_normal((n, 3 * n)); A = X @ X.T
+    Y = rng.standard_normal((n, 3 * n)); B = Y @ Y.T
+    U, D = jdiag(A, B)
+    assert np.allclose(U.T @ (B + 1e-7 * np.eye(n)) @ U, np.eye(n), atol=1e-9)
+    assert np.allclose(U.T @ A @ U, D, atol=1e-8 * np.abs(D).max())
+    assert np.all(np.diff(np.diag(D)) <= 0)
+
+
+def test_full_rank_closed_form():
+    # apVast.m:115-118 / vast.m:92: V = n  =>  w = (R_B + mu (R_D + reg I))^-1 r_B
+    eng, g, res = replay(ApvastOracle, "tiny_full")
+    n = eng.R_A_to_A.shape[0]
+    w = np.linalg.solve(eng.R_A_to_A + eng.mu * (eng.R_A_to_B + 1e-7 * np.eye(n)), eng.r_A)
+    assert np.linalg.norm(w - eng.w_A[-1]) / np.linalg.norm(w) < 1e-8
