@@ -1,0 +1,111 @@
+// Internal structures of the AP-VAST B200 engine: device state of one handle and the stage launchers.
+#pragma once
+#include "../../include/apvast_b200.h"
+#include "common.cuh"
+
+namespace apv {
+
+constexpr int STATS_KC = 64;   // K chunk of the statistics SYRK; fixes the padding of the packed s' buffer
+
+// Derived sizes.  Symbols as in SURVEY.md: Nb block, H hop, K rir length, L srcs, M mics, J taps,
+// N statistics length, V ranks, n = L*J, P = N-J columns of the data matrix, F = Nb/2+1 bins.
+struct Dims {
+  int Nb, H, K, L, M, J, N, V, d, refA, refB, runA, runB, F, n, ldn, P, Ns, LX;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Joint diagonalisation workspace (jdiag.cu); batched over `nz` zone problems of equal size.
+struct JdiagWs {
+  int n = 0, ldn = 0, V = 0, nz = 0, nb = 0, nbt = 0, eig_mode = 0;
+  double* Lm = nullptr;     // [nz][n][ldn]  R_D + reg I -> Cholesky factor (lower)
+  double* Cm = nullptr;     // [nz][n][ldn]  R_B -> C = L^-1 R_B L^-T -> (tridiagonalised in place)
+  double* Tm = nullptr;     // [nz][n][ldn]  scratch (transpose)
+  double* VH = nullptr;     // [nz][n][ldn]  Householder vectors, row j = v_j
+  double* Dinv = nullptr;   // [nz][n/nb][nb][nb] inverses of the Cholesky diagonal blocks
+  double* Z1 = nullptr;     // [nz][n][2 nbt]  [V | W] panel
+  double* Z2 = nullptr;     // [nz][n][2 nbt]  [W | V] panel
+  double* tau = nullptr;    // [nz][n]
+  double* dd = nullptr;     // [nz][n] diagonal of T
+  double* ee = nullptr;     // [nz][n] off-diagonal of T
+  double* colbuf = nullptr; // [nz][n]
+  double* ybuf = nullptr;   // [nz][n]
+  double* wbuf = nullptr;   // [nz][n]
+  double* part = nullptr;   // [nz][PARTS][2 nbt + 2] per-CTA partial sums
+  double* lam = nullptr;    // [nz][V]   top-V eigenvalues, descending
+  double* shift = nullptr;  // [nz][V]   perturbed shifts for inverse iteration
+  double* iv = nullptr;     // [nz][6][n][Vp] inverse-iteration work (interleaved over vectors)
+  double* Zt = nullptr;     // [nz][V][n] eigenvectors of T -> of C -> joint eigenvectors U (row v)
+  int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
+  int Vp = 0;
+  size_t bytes = 0;
+};
+int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode);
+void jdiag_free(JdiagWs& ws);
+// bright[z], dark[z]: device n x n matrices with leading dimension ld_in.
+int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
+              cudaStream_t st, int* launches);
+
+// ---------------------------------------------------------------------------------------------
+struct Handle {
+  apv_config cfg;
+  Dims D;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8] = {};
+  int device = 0;
+  // constants
+  double* rirT = nullptr;    // [zone 2][M][L][K]
+  double* rirTT = nullptr;   // [zone 2][M][K]     delayed target RIRs (apvast.py:102-112)
+  double* win = nullptr;     // [Nb]
+  double2* tw = nullptr;     // [Nb]  exp(-2 pi i k / Nb)
+  int nrad = 0;
+  int rad[32];
+  double* G2 = nullptr;      // [C][F] masking model table
+  int nchan = 0;
+  double Cs = 0, Ca = 0, Leff = 1;
+  // state
+  double* xin = nullptr;     // [2][LX]
+  double* Q = nullptr;       // [4][M][L][Nb]
+  double* QT = nullptr;      // [2][M][Nb]
+  double* O = nullptr;       // [4][M][L][Nb]
+  double* OT = nullptr;      // [2][M][Nb]
+  double* S = nullptr;       // [4][M][L][N]
+  double* ST = nullptr;      // [2][M][N]
+  double* Sp = nullptr;      // [4][M][L][Ns]   s' = delete(S, J), zero padded
+  double* Wg = nullptr;      // [2][M][F]
+  double* tframe = nullptr;  // [2][M][Nb]
+  double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)
+  double* G = nullptr;       // [2][V][L][Nb]
+  double* Gt = nullptr;      // [2][Nb]
+  // results
+  double* R = nullptr;       // [4][n][ldn]
+  double* rvec = nullptr;    // [2][n]
+  double* lam = nullptr;     // [2][V]
+  double* U = nullptr;       // [2][V][n]
+  double* W = nullptr;       // [2][V][n]
+  // staging
+  double* d_in = nullptr;    // [2][H]
+  double* d_out = nullptr;   // [2][V][H][L]
+  double* d_out_t = nullptr; // [2][H]
+  double* h_pin = nullptr;   // pinned host staging
+  size_t h_pin_count = 0;
+  JdiagWs jd;
+  int nz = 0;
+  int zones[2] = {0, 1};
+  float stage_ms[7] = {};
+  int launches = 0;
+  bool began = false;
+};
+
+// stage launchers (each returns status; `launches` is incremented per kernel launch)
+int stage_fir(Handle& h, const double* d_inA, const double* d_inB);           // S1 (fir_wola.cu)
+int stage_targets(Handle& h, bool compute_gain);                              // S2 + S2b
+int stage_weighted(Handle& h);                                                // S3
+int stage_stats(Handle& h);                                                   // S4 (stats.cu)
+int stage_sweep(Handle& h, double mu, double* W_out);                         // S6 (render.cu)
+int stage_render(Handle& h);                                                  // a2 + S7
+int fft_plan(int n, int* rad, int* nrad);
+int fft_util(int n, int inverse, const double* in_ri, double* out_ri);        // test hook
+
+}  // namespace apv
+
+struct apv_handle : public apv::Handle {};

@@ -1,0 +1,162 @@
+// FP64 tensor-core (DMMA m8n8k4) GEMM building block used by the joint-diagonalisation kernels
+// (blocked Cholesky trailing update, blocked triangular solves, SYR2K of the tridiagonalisation,
+// back-transformations).  Replaces the BLAS-3 calls underneath the reference's jdiag
+// (Python/apvast.py:20-36: LAPACK dpotrf/dtrtrs + BLAS dgemm/dsyrk).
+//
+// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA atoms (64 FP64 accumulators/thread),
+// register-staged double buffering of the global->shared copies, padded shared tiles so every
+// fragment load is bank-conflict free (row pitch == 4 mod 16 doubles).
+#include "common.cuh"
+
+namespace apv {
+
+thread_local char g_err[512] = {0};
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int LDK = BK + 4;    // pitch of [rows][BK] tiles      (20  == 4 mod 16)
+constexpr int LDM = BM + 4;    // pitch of [BK][rows] tiles      (132 == 4 mod 16)
+constexpr int TILE = (BM * LDK > BK * LDM) ? BM * LDK : BK * LDM;   // doubles per operand tile
+constexpr int SMEM_BYTES = 4 * TILE * (int)sizeof(double);          // 2 operands x 2 stages
+
+// Fetch 8 consecutive doubles of a row-major matrix with bounds (zero fill).
+__device__ __forceinline__ void fetch8(const double* __restrict__ P, int ld, int r, int c, int rmax, int cmax,
+                                       bool vec, double (&v)[8]) {
+  if (r < rmax && c + 7 < cmax && vec) {
+    const double2* p = reinterpret_cast<const double2*>(P + (size_t)r * ld + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double2 t = __ldg(p + i);
+      v[2 * i] = t.x;
+      v[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (r < rmax && c + i < cmax) ? __ldg(P + (size_t)r * ld + c + i) : 0.0;
+  }
+}
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256, 1) gemm_kernel(GemmArgs g) {
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.tri && n0 > m0 + BM - 1) return;
+  extern __shared__ __align__(16) double smem[];
+  double* As[2] = {smem, smem + TILE};
+  double* Bs[2] = {smem + 2 * TILE, smem + 3 * TILE};
+
+  const double* __restrict__ A = g.A + (size_t)blockIdx.z * g.strideA;
+  const double* __restrict__ B = g.B + (size_t)blockIdx.z * g.strideB;
+  double* __restrict__ C = g.C + (size_t)blockIdx.z * g.strideC;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool vecA = ((g.lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vecB = ((g.ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+  // global->shared mapping
+  //  [rows][BK] tiles: thread -> row tid>>1, cols (tid&1)*8 .. +7
+  //  [BK][rows] tiles: thread -> k-row tid>>4, cols (tid&15)*8 .. +7
+  const int rA = TA ? (tid >> 4) : (tid >> 1), cA = TA ? (tid & 15) * 8 : (tid & 1) * 8;
+  const int rB = TB ? (tid >> 1) : (tid >> 4), cB = TB ? (tid & 1) * 8 : (tid & 15) * 8;
+
+  double ra[8], rb[8];
+  auto gload = [&](int k0) {
+    if (TA) fetch8(A, g.lda, k0 + rA, m0 + cA, g.K, g.M, vecA, ra);
+    else    fetch8(A, g.lda, m0 + rA, k0 + cA, g.M, g.K, vecA, ra);
+    if (TB) fetch8(B, g.ldb, n0 + rB, k0 + cB, g.N, g.K, vecB, rb);
+    else    fetch8(B, g.ldb, k0 + rB, n0 + cB, g.K, g.N, vecB, rb);
+  };
+  auto sstore = [&](int s) {
+    double* a = As[s] + rA * (TA ? LDM : LDK) + cA;
+    double* b = Bs[s] + rB * (TB ? LDK : LDM) + cB;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      reinterpret_cast<double2*>(a)[i] = make_double2(ra[2 * i], ra[2 * i + 1]);
+      reinterpret_cast<double2*>(b)[i] = make_double2(rb[2 * i], rb[2 * i + 1]);
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (g.K + BK - 1) / BK;
+  if (nk > 0) {
+    gload(0);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+    const double* a_s = As[s];
+    const double* b_s = Bs[s];
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int rt = 0; rt < 8; ++rt)
+        a[rt] = TA ? a_s[(kk * 4 + tq) * LDM + wm + rt * 8 + gq] : a_s[(wm + rt * 8 + gq) * LDK + kk * 4 + tq];
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct)
+        b[ct] = TB ? b_s[(wn + ct * 8 + gq) * LDK + kk * 4 + tq] : b_s[(kk * 4 + tq) * LDM + wn + ct * 8 + gq];
+#pragma unroll
+      for (int rt = 0; rt < 8; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
+    }
+    if (kt + 1 < nk) sstore(s ^ 1);
+    __syncthreads();
+  }
+
+  const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+  for (int rt = 0; rt < 8; ++rt) {
+    const int r = m0 + wm + rt * 8 + gq;
+    if (r >= g.M) continue;
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+      const int c = n0 + wn + ct * 8 + 2 * tq;
+      double* p = C + (size_t)r * g.ldc + c;
+      double v0 = g.alpha * acc[rt][ct][0], v1 = g.alpha * acc[rt][ct][1];
+      if (c + 1 < g.N && vecC) {
+        if (g.beta != 0.0) {
+          double2 o = *reinterpret_cast<double2*>(p);
+          v0 += g.beta * o.x;
+          v1 += g.beta * o.y;
+        }
+        *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+      } else {
+        if (c < g.N) p[0] = v0 + (g.beta != 0.0 ? g.beta * p[0] : 0.0);
+        if (c + 1 < g.N) p[1] = v1 + (g.beta != 0.0 ? g.beta * p[1] : 0.0);
+      }
+    }
+  }
+}
+
+template <int TA, int TB>
+int launch(const GemmArgs& g, cudaStream_t st) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    APV_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.batch > 0 ? g.batch : 1);
+  gemm_kernel<TA, TB><<<grid, 256, SMEM_BYTES, st>>>(g);
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
+}  // namespace
+
+int gemm_f64(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return OK;
+  if (g.transA) return g.transB ? launch<1, 1>(g, st) : launch<1, 0>(g, st);
+  return g.transB ? launch<0, 1>(g, st) : launch<0, 0>(g, st);
+}
+
+}  // namespace apv

@@ -1,0 +1,883 @@
+// S5  jdiag -- joint diagonalisation of (R_B, R_D) (reference jdiag, Python/apvast.py:20-36;
+// spec Matlab/ControlMethods/jdiag.m:103-116):
+//     Bc = chol(R_D + reg I)             -> chol_f64   (blocked right-looking, DMMA trailing update)
+//     C  = Bc^-1 R_B Bc^-T               -> trsm_f64   (blocked, diagonal-block inverses + DMMA GEMM)
+//     C  = Q Lambda Q^T                  -> syevd_f64  (blocked Householder tridiagonalisation, then
+//                                           top-V eigenpairs of T by multisection bisection and
+//                                           inverse iteration, back-transformed by the reflectors)
+//     U  = Bc^-T Q, columns sorted by descending eigenvalue
+// The reference calls a non-symmetric real Schur (LAPACK dgees) on a matrix that is symmetric to
+// rounding; here C is symmetrised and a symmetric eigensolver is used.  Only the V leading pairs
+// are formed, because calculate_filter_spectra (apvast.py:406-414) consumes U[:, :V] only.
+// Both zone problems are batched in every launch (blockIdx.y / blockIdx.z = zone).
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "engine.cuh"
+
+namespace apv {
+
+namespace {
+
+constexpr int NB = 64;    // Cholesky / TRSM block size
+constexpr int NBT = 32;   // tridiagonalisation panel width (one V and one W column per lane)
+constexpr int GMAX = 64;  // CTAs per zone for the per-column kernels
+constexpr int PSTRIDE = 2 * NBT + 2;
+
+struct Ptr2 {
+  const double* p[2];
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_kernel(Ptr2 bright, Ptr2 dark, int ld_in, double* __restrict__ Cm, double* __restrict__ Lm,
+                            int n, int ldn, double reg) {
+  const int z = blockIdx.z;
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t o = ((size_t)z * n + i) * ldn + j;
+  Cm[o] = bright.p[z][(size_t)i * ld_in + j];
+  Lm[o] = dark.p[z][(size_t)i * ld_in + j] + (i == j ? reg : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky of one diagonal block (<= NB x NB) in shared memory + its inverse.  grid (nz).
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ Lm, double* __restrict__ Dinv, int n,
+                                                        int ldn, int k0, int nbk, int nblk, int* __restrict__ info) {
+  extern __shared__ double chol_sm[];
+  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(chol_sm);
+  double (*Iv)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(chol_sm + NB * (NB + 1));
+  const int z = blockIdx.x, tid = threadIdx.x;
+  double* A = Lm + (size_t)z * n * ldn + (size_t)k0 * ldn + k0;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    As[i][j] = (i < nbk && j < nbk && j <= i) ? A[(size_t)i * ldn + j] : 0.0;
+    Iv[i][j] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < nbk; ++j) {
+    if (tid == 0) {
+      double d = As[j][j];
+      if (!(d > 0.0)) {                       // also catches NaN
+        if (info[z * 4] == 0) info[z * 4] = k0 + j + 1;
+        d = 1.0;
+      }
+      As[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = As[j][j];
+    for (int i = j + 1 + tid; i < nbk; i += blockDim.x) As[i][j] /= dj;
+    __syncthreads();
+    const int m = nbk - j - 1;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int i = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= i) As[i][c] -= As[i][j] * As[c][j];
+    }
+    __syncthreads();
+  }
+  // inverse of the lower-triangular block, one column per thread
+  if (tid < nbk) {
+    const int c = tid;
+    for (int i = c; i < nbk; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= As[i][k] * Iv[k][c];
+      Iv[i][c] = s / As[i][i];
+    }
+  }
+  __syncthreads();
+  double* Di = Dinv + ((size_t)z * nblk + k0 / NB) * NB * NB;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    Di[e] = Iv[i][j];
+    if (i < nbk && j < nbk) A[(size_t)i * ldn + j] = As[i][j];   // lower factor, zeros above the diagonal
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out = in^T (per zone), 32x32 tiles.
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n, int ldn) {
+  __shared__ double t[32][33];
+  const size_t zo = (size_t)blockIdx.z * n * ldn;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    t[r][threadIdx.x] = (i < n && j < n) ? in[zo + (size_t)i * ldn + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;
+    if (i < n && j < n) out[zo + (size_t)i * ldn + j] = t[threadIdx.x][r];
+  }
+}
+
+// out = (in + in^T) / 2 (per zone).
+__global__ void symmetrize_kernel(const double* __restrict__ in, double* __restrict__ out, int n, int ldn) {
+  __shared__ double t[32][33];
+  const size_t zo = (size_t)blockIdx.z * n * ldn;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;     // transposed tile
+    t[r][threadIdx.x] = (i < n && j < n) ? in[zo + (size_t)i * ldn + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    if (i < n && j < n) out[zo + (size_t)i * ldn + j] = 0.5 * (in[zo + (size_t)i * ldn + j] + t[threadIdx.x][r]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tridiagonalisation, per-column kernels (lower variant of LAPACK dlatrd, full symmetric storage).
+// Panel storage: Z1[i][0..NBT) = V, Z1[i][NBT..2NBT) = W;  Z2[i][0..NBT) = W, Z2[i][NBT..2NBT) = V.
+// part[z][g][0] partial of |x[j+2:]|^2, [1] partial of w.v, [2 + col] partials of (panel col)^T v.
+struct TdArgs {
+  double* Cm; double* VH; double* Z1; double* Z2; double* tau; double* dd; double* ee;
+  double* colbuf; double* ybuf; double* wbuf; double* part;
+  int n, ldn;
+};
+
+__device__ __forceinline__ void chunk_of(int lo, int hi, int G, int g, int& a, int& b) {
+  const int rows = hi - lo, per = (rows + G - 1) / G;
+  a = lo + g * per;
+  b = min(hi, a + per);
+}
+
+// (1) finish w of the previous column (jj > 0) and form the updated column j:  x = A[j, j:n] - corrections.
+// mode 0: both; mode 1: finalise only (end of panel).  grid (G, nz); Gprev = grid.x of the previous td_w_kernel.
+__global__ void __launch_bounds__(256) td_col_kernel(TdArgs a, int j, int jj, int Gprev, int mode) {
+  __shared__ double sh_gamma;
+  const int z = blockIdx.y, g = blockIdx.x, G = gridDim.x, n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
+  double* part = a.part + (size_t)z * GMAX * PSTRIDE;
+  const double* Cm = a.Cm + (size_t)z * n * a.ldn;
+  double* colbuf = a.colbuf + (size_t)z * n;
+  const double* wbuf = a.wbuf + (size_t)z * n;
+  double gamma = 0.0;
+  if (jj > 0) {
+    if (warp == 0) {
+      double s = 0.0;
+      for (int q = lane; q < Gprev; q += 32) s += part[q * PSTRIDE + 1];
+      s = warp_sum(s);
+      if (lane == 0) sh_gamma = 0.5 * a.tau[(size_t)z * n + j - 1] * s;
+    }
+    __syncthreads();
+    gamma = sh_gamma;
+  }
+  int r0, r1;
+  chunk_of(j, n, G, g, r0, r1);
+  // row-j panel entries (needed by every row): lane c holds V[j][c], W[j][c]
+  double Vj = 0.0, Wj = 0.0;
+  if (mode == 0 && lane < jj) {
+    if (lane < jj - 1) {
+      Vj = Z1[(size_t)j * 2 * NBT + lane];
+      Wj = Z1[(size_t)j * 2 * NBT + NBT + lane];
+    } else {                      // column jj-1: v_{j-1}[j] = 1, w finalised on the fly
+      Vj = 1.0;
+      Wj = wbuf[j] - gamma;
+    }
+  }
+  double xsq = 0.0;
+  for (int i = r0 + warp; i < r1; i += 8) {
+    double wfin = 0.0, vprev = 0.0;
+    if (jj > 0) {
+      vprev = Z1[(size_t)i * 2 * NBT + jj - 1];
+      wfin = wbuf[i] - gamma * vprev;
+      if (lane == 0) {
+        Z1[(size_t)i * 2 * NBT + NBT + jj - 1] = wfin;
+        Z2[(size_t)i * 2 * NBT + jj - 1] = wfin;
+      }
+    }
+    if (mode == 0) {
+      double corr = 0.0;
+      if (lane < jj) {
+        double Vi, Wi;
+        if (lane < jj - 1) {
+          Vi = Z1[(size_t)i * 2 * NBT + lane];
+          Wi = Z1[(size_t)i * 2 * NBT + NBT + lane];
+        } else {
+          Vi = vprev;
+          Wi = wfin;
+        }
+        corr = Vi * Wj + Wi * Vj;
+      }
+      corr = warp_sum(corr);
+      if (lane == 0) {
+        const double x = Cm[(size_t)j * a.ldn + i] - corr;
+        colbuf[i] = x;
+        if (i == j) a.dd[(size_t)z * n + j] = x;
+        if (i >= j + 2) xsq += x * x;
+      }
+    }
+  }
+  if (mode == 0) {
+    __shared__ double red[8];
+    if (lane == 0) red[warp] = xsq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      part[g * PSTRIDE + 0] = s;
+    }
+  }
+}
+
+// (2) reflector from the updated column, y = A[j+1:, j+1:] v, partial panel^T v.  grid (G, nz), Gcol = grid.x of
+// the td_col_kernel launch.  Dynamic shared memory: (n - j - 1) doubles.
+__global__ void __launch_bounds__(256) td_gemv_kernel(TdArgs a, int j, int jj, int Gcol) {
+  extern __shared__ double vs[];
+  __shared__ double sh[3];
+  __shared__ double tred[4][2 * NBT];
+  const int z = blockIdx.y, g = blockIdx.x, G = gridDim.x, n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
+  double* part = a.part + (size_t)z * GMAX * PSTRIDE;
+  const double* Cm = a.Cm + (size_t)z * n * a.ldn;
+  const double* colbuf = a.colbuf + (size_t)z * n;
+  if (warp == 0) {
+    double s = 0.0;
+    for (int q = lane; q < Gcol; q += 32) s += part[q * PSTRIDE + 0];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const double alpha = colbuf[j + 1];
+      const double xnorm = sqrt(s);
+      double beta, tau, scal;
+      if (xnorm == 0.0) {
+        beta = alpha; tau = 0.0; scal = 0.0;
+      } else {
+        beta = -copysign(hypot(alpha, xnorm), alpha);
+        tau = (beta - alpha) / beta;
+        scal = 1.0 / (alpha - beta);
+      }
+      sh[0] = beta; sh[1] = tau; sh[2] = scal;
+      if (g == 0) {
+        a.ee[(size_t)z * n + j] = beta;
+        a.tau[(size_t)z * n + j] = tau;
+      }
+    }
+  }
+  __syncthreads();
+  const double scal = sh[2];
+  const int m = n - j - 1;                       // trailing size; vs[k] = v[j+1+k]
+  for (int k = threadIdx.x; k < m; k += blockDim.x) vs[k] = (k == 0) ? 1.0 : colbuf[j + 1 + k] * scal;
+  __syncthreads();
+  int r0, r1;
+  chunk_of(j + 1, n, G, g, r0, r1);
+  double* VHj = a.VH + (size_t)z * n * a.ldn + (size_t)j * a.ldn;
+  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    const double v = vs[i - j - 1];
+    VHj[i] = v;
+    Z1[(size_t)i * 2 * NBT + jj] = v;
+    Z2[(size_t)i * 2 * NBT + NBT + jj] = v;
+  }
+  // GEMV rows: warp per row
+  double* ybuf = a.ybuf + (size_t)z * n;
+  for (int i = r0 + warp; i < r1; i += 8) {
+    const double* row = Cm + (size_t)i * a.ldn + j + 1;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = lane;
+    for (; k + 32 < m; k += 64) {
+      acc0 = fma(row[k], vs[k], acc0);
+      acc1 = fma(row[k + 32], vs[k + 32], acc1);
+    }
+    if (k < m) acc0 = fma(row[k], vs[k], acc0);
+    const double s = warp_sum(acc0 + acc1);
+    if (lane == 0) ybuf[i] = s;
+  }
+  // partial panel^T v over this CTA's rows (columns with (col % NBT) < jj; col jj of V is v itself, unused)
+  if (jj > 0) {
+    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    double acc = 0.0;
+    if ((col & (NBT - 1)) < jj)
+      for (int i = r0 + rg; i < r1; i += 4) acc = fma(Z1[(size_t)i * 2 * NBT + col], vs[i - j - 1], acc);
+    tred[rg][col] = acc;
+    __syncthreads();
+    if (threadIdx.x < 2 * NBT)
+      part[g * PSTRIDE + 2 + threadIdx.x] = tred[0][threadIdx.x] + tred[1][threadIdx.x] + tred[2][threadIdx.x] +
+                                            tred[3][threadIdx.x];
+  }
+}
+
+// (3) w = tau (y - V (W^T v) - W (V^T v)), partial w.v.  grid (G, nz) with the SAME G as td_gemv_kernel.
+__global__ void __launch_bounds__(256) td_w_kernel(TdArgs a, int j, int jj) {
+  __shared__ double ts[2 * NBT];
+  __shared__ double red[8];
+  const int z = blockIdx.y, g = blockIdx.x, G = gridDim.x, n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  double* part = a.part + (size_t)z * GMAX * PSTRIDE;
+  if (threadIdx.x < 2 * NBT) {
+    double s = 0.0;
+    if (jj > 0 && (threadIdx.x & (NBT - 1)) < jj)
+      for (int q = 0; q < G; ++q) s += part[q * PSTRIDE + 2 + threadIdx.x];
+    ts[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const double tau = a.tau[(size_t)z * n + j];
+  int r0, r1;
+  chunk_of(j + 1, n, G, g, r0, r1);
+  const double* ybuf = a.ybuf + (size_t)z * n;
+  double* wbuf = a.wbuf + (size_t)z * n;
+  double wv = 0.0;
+  for (int i = r0 + warp; i < r1; i += 8) {
+    double corr = 0.0;
+    if (lane < jj) corr = Z1[(size_t)i * 2 * NBT + lane] * ts[NBT + lane] + Z1[(size_t)i * 2 * NBT + NBT + lane] * ts[lane];
+    corr = warp_sum(corr);
+    if (lane == 0) {
+      const double w = tau * (ybuf[i] - corr);
+      wbuf[i] = w;
+      wv += w * Z1[(size_t)i * 2 * NBT + jj];
+    }
+  }
+  if (lane == 0) red[warp] = wv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    part[g * PSTRIDE + 1] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Top-V eigenvalues of the symmetric tridiagonal (dd, ee) by multisection (32 Sturm counts per pass, one
+// warp per eigenvalue).  Count recurrence as LAPACK dlaebz.  grid (ceil(V/8), nz); smem 2n doubles.
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n,
+                                           double x, double pivmin) {
+  double t = d[0] - x;
+  if (fabs(t) < pivmin) t = -pivmin;
+  int c = (t <= 0.0);
+  for (int i = 1; i < n; ++i) {
+    t = d[i] - e2[i - 1] / t - x;
+    if (fabs(t) < pivmin) t = -pivmin;
+    c += (t <= 0.0);
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) eig_bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee,
+                                                         double* __restrict__ lam, double* __restrict__ tnorm, int n,
+                                                         int V) {
+  extern __shared__ double sm[];
+  double* d = sm;
+  double* e2 = sm + n;
+  __shared__ double red[40];
+  __shared__ double sh[4];
+  const int z = blockIdx.y;
+  const double* gd = dd + (size_t)z * n;
+  const double* ge = ee + (size_t)z * n;
+  double gl = DBL_MAX, gu = -DBL_MAX, emax = 0.0, onenrm = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double di = gd[i];
+    const double el = i > 0 ? fabs(ge[i - 1]) : 0.0, er = i < n - 1 ? fabs(ge[i]) : 0.0;
+    d[i] = di;
+    e2[i] = i < n - 1 ? ge[i] * ge[i] : 0.0;
+    gl = fmin(gl, di - el - er);
+    gu = fmax(gu, di + el + er);
+    emax = fmax(emax, er * er);
+    onenrm = fmax(onenrm, fabs(di) + el + er);
+  }
+  // block min/max via negated sums is awkward; do simple shared reductions
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+    gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+    emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    onenrm = fmax(onenrm, __shfl_xor_sync(0xffffffffu, onenrm, o));
+  }
+  if (lane == 0) { red[warp] = gl; red[8 + warp] = gu; red[16 + warp] = emax; red[24 + warp] = onenrm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      red[0] = fmin(red[0], red[w]); red[8] = fmax(red[8], red[8 + w]);
+      red[16] = fmax(red[16], red[16 + w]); red[24] = fmax(red[24], red[24 + w]);
+    }
+    const double tn = fmax(fabs(red[0]), fabs(red[8]));
+    sh[0] = red[0] - 2.1 * tn * DBL_EPSILON * n - 4.2 * DBL_MIN;   // dstebz widening
+    sh[1] = red[8] + 2.1 * tn * DBL_EPSILON * n + 4.2 * DBL_MIN;
+    sh[2] = DBL_MIN * fmax(1.0, red[16]);                          // pivmin
+    sh[3] = red[24];
+    if (blockIdx.x == 0) { tnorm[z * 4 + 0] = red[24]; tnorm[z * 4 + 1] = sh[2]; tnorm[z * 4 + 2] = tn; }
+  }
+  __syncthreads();
+  const int v = blockIdx.x * 8 + warp;
+  if (v >= V) return;
+  const int k = n - v;            // k-th smallest (1-based)
+  double lo = sh[0], hi = sh[1];
+  const double pivmin = sh[2];
+  const double atol = DBL_EPSILON * fmax(fabs(lo), fabs(hi));
+  for (int it = 0; it < 200; ++it) {
+    const double width = hi - lo;
+    if (width <= fmax(fmax(atol, pivmin), 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)))) break;
+    const double h = width / 33.0;
+    const double x = lo + (lane + 1) * h;
+    const int c = sturm_count(d, e2, n, x, pivmin);
+    const unsigned mask = __ballot_sync(0xffffffffu, c >= k);
+    double nlo, nhi;
+    if (mask == 0u) {
+      nlo = __shfl_sync(0xffffffffu, x, 31);
+      nhi = hi;
+    } else {
+      const int f = __ffs(mask) - 1;
+      nhi = __shfl_sync(0xffffffffu, x, f);
+      nlo = f > 0 ? __shfl_sync(0xffffffffu, x, f - 1) : lo;
+    }
+    if (!(nhi - nlo < width)) break;     // no progress at working precision
+    lo = nlo; hi = nhi;
+  }
+  if (lane == 0) lam[(size_t)z * V + v] = 0.5 * (lo + hi);
+}
+
+// Shifts for inverse iteration: ascending walk, close values pushed apart by 10 eps |x| (LAPACK dstein).
+__global__ void eig_shift_kernel(const double* __restrict__ lam, double* __restrict__ shift, int V) {
+  const int z = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double xjm = 0.0;
+  for (int v = V - 1; v >= 0; --v) {        // lam is descending -> walk ascending
+    double xj = lam[(size_t)z * V + v];
+    if (v < V - 1) {
+      const double pertol = 10.0 * fabs(DBL_EPSILON * xj);
+      if (xj - xjm < pertol) xj = xjm + pertol;
+    }
+    shift[(size_t)z * V + v] = xj;
+    xjm = xj;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverse iteration, one thread per eigenvector (LAPACK dstein with dlagtf / dlagts(job=-1) restated).
+// Work arrays are interleaved over vectors: arr[i * Vp + v].  grid (Vp/32, nz), 32 threads.
+__device__ __forceinline__ double urand(unsigned long long& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  unsigned long long x = s;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+__global__ void __launch_bounds__(32) eig_invit_kernel(const double* __restrict__ dd, const double* __restrict__ ee,
+                                                       const double* __restrict__ shift,
+                                                       const double* __restrict__ tnorm, double* __restrict__ iv,
+                                                       int* __restrict__ info, int n, int V, int Vp) {
+  const int z = blockIdx.y;
+  const int v = blockIdx.x * 32 + threadIdx.x;
+  if (v >= V) return;
+  const double* d = dd + (size_t)z * n;
+  const double* e = ee + (size_t)z * n;
+  double* base = iv + (size_t)z * 6 * n * Vp;
+  double* A = base + 0 * (size_t)n * Vp + v;
+  double* B = base + 1 * (size_t)n * Vp + v;
+  double* C = base + 2 * (size_t)n * Vp + v;
+  double* D2 = base + 3 * (size_t)n * Vp + v;
+  double* X = base + 4 * (size_t)n * Vp + v;
+  double* IN = base + 5 * (size_t)n * Vp + v;
+  const size_t S = (size_t)Vp;
+  const double lamv = shift[(size_t)z * V + v];
+  const double onenrm = tnorm[z * 4 + 0];
+  const double eps = DBL_EPSILON;
+  unsigned long long seed = 0x1234567ull + 7919ull * (unsigned long long)v + 104729ull * (unsigned long long)z;
+
+  if (n == 1) {
+    X[0] = 1.0;
+    return;
+  }
+  // ---- dlagtf: T - lam I = P L U
+  double ak = d[0] - lamv;
+  double bk = e[0];
+  double tolmax = 0.0;
+  double scale1 = fabs(ak) + fabs(bk);
+  for (int k = 0; k < n - 1; ++k) {
+    double ak1 = d[k + 1] - lamv;
+    const double ck = e[k];
+    const double bk1 = (k < n - 2) ? e[k + 1] : 0.0;
+    double scale2 = fabs(ck) + fabs(ak1);
+    if (k < n - 2) scale2 += fabs(bk1);
+    const double piv1 = (ak == 0.0) ? 0.0 : fabs(ak) / scale1;
+    double cout, dout = 0.0, inflag = 0.0, bnext = bk1;
+    if (ck == 0.0) {
+      scale1 = scale2;
+      cout = 0.0;
+    } else {
+      const double piv2 = fabs(ck) / scale2;
+      if (piv2 <= piv1) {
+        scale1 = scale2;
+        cout = ck / ak;
+        ak1 -= cout * bk;
+      } else {
+        inflag = 1.0;
+        const double mult = ak / ck;
+        ak = ck;
+        const double temp = ak1;
+        ak1 = bk - mult * temp;
+        if (k < n - 2) {
+          dout = bk1;
+          bnext = -mult * dout;
+        }
+        bk = temp;
+        cout = mult;
+      }
+    }
+    A[k * S] = ak; B[k * S] = bk; C[k * S] = cout; D2[k * S] = dout; IN[k * S] = inflag;
+    tolmax = fmax(tolmax, fmax(fabs(ak), fmax(fabs(bk), fabs(dout))));
+    ak = ak1;
+    bk = bnext;
+  }
+  A[(size_t)(n - 1) * S] = ak;
+  tolmax = fmax(tolmax, fabs(ak));
+  const double alast = ak;
+  double tol = tolmax * eps;
+  if (tol == 0.0) tol = eps;
+  const double sfmin = DBL_MIN, bignum = 1.0 / DBL_MIN;
+
+  // ---- iterations
+  for (int i = 0; i < n; ++i) X[i * S] = urand(seed);
+  const double dtpcrt = sqrt(0.1 / n);
+  int nrmchk = 0, its = 0;
+  bool ok = false;
+  while (its < 8) {
+    ++its;
+    double xmax = 0.0;
+    for (int i = 0; i < n; ++i) xmax = fmax(xmax, fabs(X[i * S]));
+    const double scl = n * onenrm * fmax(eps, fabs(alast)) / xmax;
+    // forward elimination (with the scaling folded in)
+    double prev = X[0] * scl;
+    for (int k = 1; k < n; ++k) {
+      const double xk = X[k * S] * scl;
+      const double c = C[(k - 1) * S];
+      if (IN[(k - 1) * S] == 0.0) {
+        X[(k - 1) * S] = prev;
+        prev = xk - c * prev;
+      } else {
+        X[(k - 1) * S] = xk;
+        prev = prev - c * xk;
+      }
+    }
+    X[(size_t)(n - 1) * S] = prev;
+    // back substitution with pivot perturbation (dlagts job = -1)
+    double y1 = 0.0, y2 = 0.0;        // x[k+1], x[k+2]
+    for (int k = n - 1; k >= 0; --k) {
+      double temp = X[k * S];
+      if (k <= n - 3) temp = temp - B[k * S] * y1 - D2[k * S] * y2;
+      else if (k == n - 2) temp = temp - B[k * S] * y1;
+      double akk = A[k * S];
+      double pert = copysign(tol, akk);
+      for (;;) {
+        const double absak = fabs(akk);
+        if (absak < 1.0) {
+          if (absak < sfmin) {
+            if (absak == 0.0 || fabs(temp) * sfmin > absak) { akk += pert; pert *= 2.0; continue; }
+            temp *= bignum; akk *= bignum;
+          } else if (fabs(temp) > absak * bignum) { akk += pert; pert *= 2.0; continue; }
+        }
+        break;
+      }
+      const double xk = temp / akk;
+      X[k * S] = xk;
+      y2 = y1; y1 = xk;
+    }
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) nrm = fmax(nrm, fabs(X[i * S]));
+    if (nrm < dtpcrt) continue;
+    if (++nrmchk < 3) continue;
+    ok = true;
+    break;
+  }
+  if (!ok) atomicOr(&info[z * 4 + 1], 1);
+  double ss = 0.0;
+  for (int i = 0; i < n; ++i) { const double t = X[i * S]; ss += t * t; }
+  const double inv = 1.0 / sqrt(ss);
+  for (int i = 0; i < n; ++i) X[i * S] *= inv;
+}
+
+// Re-orthogonalise eigenvectors whose eigenvalues are (nearly) degenerate: modified Gram-Schmidt inside each
+// run of consecutive eigenvalues closer than ctol * |T|.  One CTA per zone.
+__global__ void __launch_bounds__(256) eig_cluster_mgs_kernel(const double* __restrict__ lam,
+                                                              const double* __restrict__ tnorm,
+                                                              double* __restrict__ iv, int n, int V, int Vp, double ctol) {
+  __shared__ double red[40];
+  const int z = blockIdx.x;
+  double* X = iv + (size_t)z * 6 * n * Vp + 4 * (size_t)n * Vp;
+  const double thr = ctol * tnorm[z * 4 + 0];
+  int start = V - 1;                      // ascending walk: v = V-1 (smallest) .. 0
+  for (int v = V - 2; v >= 0; --v) {
+    const bool close = fabs(lam[(size_t)z * V + v] - lam[(size_t)z * V + v + 1]) <= thr;
+    if (!close) { start = v; continue; }
+    for (int u = start; u > v; --u) {     // orthogonalise x_v against x_u, u in the same cluster
+      double s = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s += X[(size_t)i * Vp + v] * X[(size_t)i * Vp + u];
+      s = block_sum(s, red);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) X[(size_t)i * Vp + v] -= s * X[(size_t)i * Vp + u];
+      __syncthreads();
+    }
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double t = X[(size_t)i * Vp + v]; s += t * t; }
+    s = block_sum(s, red);
+    const double inv = 1.0 / sqrt(s);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) X[(size_t)i * Vp + v] *= inv;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q = H_0 H_1 ... H_{n-3} z  (apply reflectors in reverse order), one CTA per eigenvector.  grid (V, nz).
+__global__ void __launch_bounds__(256) eig_backtransform_kernel(const double* __restrict__ iv,
+                                                                const double* __restrict__ VH,
+                                                                const double* __restrict__ tau,
+                                                                double* __restrict__ Zt, int n, int ldn, int V, int Vp) {
+  extern __shared__ double xs[];
+  __shared__ double red[2][8];
+  const int v = blockIdx.x, z = blockIdx.y;
+  const double* X = iv + (size_t)z * 6 * n * Vp + 4 * (size_t)n * Vp + v;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = X[(size_t)i * Vp];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* vh = VH + (size_t)z * n * ldn;
+  const double* tz = tau + (size_t)z * n;
+  int par = 0;
+  for (int j = n - 2; j >= 0; --j) {
+    const double t = tz[j];
+    if (t == 0.0) continue;               // uniform across the CTA
+    const double* vj = vh + (size_t)j * ldn;
+    // fixed ownership i == threadIdx.x (mod 256) so xs needs no barrier between reflectors
+    int i0 = threadIdx.x;
+    if (i0 <= j) i0 += ((j - i0) / 256 + 1) * 256;
+    double s = 0.0;
+    for (int i = i0; i < n; i += 256) s = fma(vj[i], xs[i], s);
+    s = warp_sum(s);
+    if (lane == 0) red[par][warp] = s;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[par][w];
+    tot *= t;
+    for (int i = i0; i < n; i += 256) xs[i] = fma(-tot, vj[i], xs[i]);
+    par ^= 1;
+  }
+  __syncthreads();
+  double* out = Zt + ((size_t)z * V + v) * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = xs[i];
+}
+
+// u = L^-T q for each eigenvector (back substitution, row-oriented), one CTA per vector.  grid (V, nz).
+__global__ void __launch_bounds__(256) eig_backsolve_kernel(const double* __restrict__ Lm, double* __restrict__ Zt,
+                                                            int n, int ldn, int V) {
+  extern __shared__ double xs[];
+  __shared__ double us[32];
+  const int v = blockIdx.x, z = blockIdx.y;
+  double* q = Zt + ((size_t)z * V + v) * n;
+  const double* L = Lm + (size_t)z * n * ldn;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = q[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b1 = n; b1 > 0; b1 -= 32) {
+    const int b0 = max(0, b1 - 32), bs = b1 - b0;
+    if (warp == 0) {
+      // triangular solve of the bs x bs diagonal block, lane r' owns xs[b0 + r']
+      double mine = lane < bs ? xs[b0 + lane] : 0.0;
+      for (int r = bs - 1; r >= 0; --r) {
+        const double num = __shfl_sync(0xffffffffu, mine, r);
+        const double ur = num / L[(size_t)(b0 + r) * ldn + b0 + r];
+        if (lane == r) mine = ur;
+        else if (lane < r) mine -= ur * L[(size_t)(b0 + r) * ldn + b0 + lane];
+      }
+      if (lane < bs) { xs[b0 + lane] = mine; us[lane] = mine; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < b0; c += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < bs; ++r) acc = fma(us[r], L[(size_t)(b0 + r) * ldn + c], acc);
+      xs[c] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] = xs[i];
+}
+
+template <typename Kern>
+int ensure_smem(Kern k, size_t bytes) {
+  if (bytes > 48 * 1024) APV_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
+  ws.n = n; ws.V = V; ws.nz = nz; ws.nb = NB; ws.nbt = NBT; ws.eig_mode = eig_mode;
+  ws.ldn = round_up(n, 8);
+  ws.Vp = round_up(V, 32);
+  const size_t mat = (size_t)nz * n * ws.ldn * sizeof(double);
+  const int nblk = ceil_div(n, NB);
+  size_t total = 0;
+  auto al = [&](void** p, size_t bytes) -> int {
+    APV_CUDA_TRY(cudaMalloc(p, bytes));
+    APV_CUDA_TRY(cudaMemset(*p, 0, bytes));
+    total += bytes;
+    return OK;
+  };
+  APV_TRY(al((void**)&ws.Lm, mat));
+  APV_TRY(al((void**)&ws.Cm, mat));
+  APV_TRY(al((void**)&ws.Tm, mat));
+  APV_TRY(al((void**)&ws.VH, mat));
+  APV_TRY(al((void**)&ws.Dinv, (size_t)nz * nblk * NB * NB * sizeof(double)));
+  APV_TRY(al((void**)&ws.Z1, (size_t)nz * n * 2 * NBT * sizeof(double)));
+  APV_TRY(al((void**)&ws.Z2, (size_t)nz * n * 2 * NBT * sizeof(double)));
+  const size_t vec = (size_t)nz * n * sizeof(double);
+  APV_TRY(al((void**)&ws.tau, vec));
+  APV_TRY(al((void**)&ws.dd, vec));
+  APV_TRY(al((void**)&ws.ee, vec));
+  APV_TRY(al((void**)&ws.colbuf, vec));
+  APV_TRY(al((void**)&ws.ybuf, vec));
+  APV_TRY(al((void**)&ws.wbuf, vec));
+  APV_TRY(al((void**)&ws.part, (size_t)nz * GMAX * PSTRIDE * sizeof(double) + 64 * sizeof(double)));
+  APV_TRY(al((void**)&ws.lam, (size_t)nz * V * sizeof(double)));
+  APV_TRY(al((void**)&ws.shift, (size_t)nz * V * sizeof(double) + (size_t)nz * 4 * sizeof(double)));
+  APV_TRY(al((void**)&ws.iv, (size_t)nz * 6 * n * ws.Vp * sizeof(double)));
+  APV_TRY(al((void**)&ws.Zt, (size_t)nz * V * n * sizeof(double)));
+  APV_TRY(al((void**)&ws.info, (size_t)nz * 4 * sizeof(int)));
+  ws.bytes = total;
+  return OK;
+}
+
+void jdiag_free(JdiagWs& ws) {
+  void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
+                ws.ybuf, ws.wbuf, ws.part, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
+  for (void* p : ps)
+    if (p) cudaFree(p);
+  ws = JdiagWs();
+}
+
+// X <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones.
+static int trsm_lower(JdiagWs& ws, double* X, int m, int ldx, long long strideX, cudaStream_t st, int* launches) {
+  const int n = ws.n, ldn = ws.ldn, nblk = ceil_div(n, NB);
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nbk = std::min(NB, n - k0);
+    GemmArgs g{};
+    g.batch = ws.nz;
+    // X_k <- Linv_kk X_k (in place: one row tile, each CTA owns its columns)
+    g.A = ws.Dinv + (size_t)(k0 / NB) * NB * NB; g.lda = NB; g.strideA = (long long)nblk * NB * NB;
+    g.B = X + (size_t)k0 * ldx; g.ldb = ldx; g.strideB = strideX;
+    g.C = X + (size_t)k0 * ldx; g.ldc = ldx; g.strideC = strideX;
+    g.M = nbk; g.N = m; g.K = nbk; g.alpha = 1.0; g.beta = 0.0;
+    APV_TRY(gemm_f64(g, st));
+    ++*launches;
+    const int rem = n - k0 - nbk;
+    if (rem > 0) {
+      GemmArgs u{};
+      u.batch = ws.nz;
+      u.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; u.lda = ldn; u.strideA = (long long)n * ldn;
+      u.B = X + (size_t)k0 * ldx; u.ldb = ldx; u.strideB = strideX;
+      u.C = X + (size_t)(k0 + nbk) * ldx; u.ldc = ldx; u.strideC = strideX;
+      u.M = rem; u.N = m; u.K = nbk; u.alpha = -1.0; u.beta = 1.0;
+      APV_TRY(gemm_f64(u, st));
+      ++*launches;
+    }
+  }
+  return OK;
+}
+
+int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
+              cudaStream_t st, int* launches) {
+  const int n = ws.n, ldn = ws.ldn, nz = ws.nz, V = ws.V;
+  const long long mstride = (long long)n * ldn;
+  int nl = 0;
+  APV_CUDA_TRY(cudaMemsetAsync(ws.info, 0, (size_t)nz * 4 * sizeof(int), st));
+  Ptr2 pb, pd;
+  for (int z = 0; z < 2; ++z) { pb.p[z] = bright[z < nz ? z : 0]; pd.p[z] = dark[z < nz ? z : 0]; }
+  prep_kernel<<<dim3(ceil_div(n, 256), n, nz), 256, 0, st>>>(pb, pd, ld_in, ws.Cm, ws.Lm, n, ldn, reg);
+  ++nl;
+
+  // ---- blocked Cholesky of Lm (lower)
+  const int nblk = ceil_div(n, NB);
+  const size_t chol_smem = (size_t)2 * NB * (NB + 1) * sizeof(double);
+  APV_TRY(ensure_smem(chol_diag_kernel, chol_smem));
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nbk = std::min(NB, n - k0);
+    chol_diag_kernel<<<nz, 256, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
+    ++nl;
+    const int rem = n - k0 - nbk;
+    if (rem > 0) {
+      GemmArgs p{};          // L21 = A21 * Linv11^T   (in place: one column tile)
+      p.batch = nz;
+      p.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.lda = ldn; p.strideA = mstride;
+      p.B = ws.Dinv + (size_t)(k0 / NB) * NB * NB; p.ldb = NB; p.strideB = (long long)nblk * NB * NB;
+      p.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.ldc = ldn; p.strideC = mstride;
+      p.M = rem; p.N = nbk; p.K = nbk; p.transB = 1; p.alpha = 1.0; p.beta = 0.0;
+      APV_TRY(gemm_f64(p, st));
+      GemmArgs u{};          // A22 -= L21 L21^T  (lower tiles)
+      u.batch = nz;
+      u.A = p.C; u.lda = ldn; u.strideA = mstride;
+      u.B = p.C; u.ldb = ldn; u.strideB = mstride;
+      u.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0 + nbk; u.ldc = ldn; u.strideC = mstride;
+      u.M = rem; u.N = rem; u.K = nbk; u.transB = 1; u.tri = 1; u.alpha = -1.0; u.beta = 1.0;
+      APV_TRY(gemm_f64(u, st));
+      nl += 2;
+    }
+  }
+
+  // ---- C = L^-1 A L^-T, symmetrised
+  APV_TRY(trsm_lower(ws, ws.Cm, n, ldn, mstride, st, &nl));
+  dim3 tb(32, 8), tg(ceil_div(n, 32), ceil_div(n, 32), nz);
+  transpose_kernel<<<tg, tb, 0, st>>>(ws.Cm, ws.Tm, n, ldn);
+  ++nl;
+  APV_TRY(trsm_lower(ws, ws.Tm, n, ldn, mstride, st, &nl));
+  symmetrize_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);
+  ++nl;
+
+  // ---- blocked Householder tridiagonalisation of Cm
+  TdArgs ta{ws.Cm, ws.VH, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf, ws.ybuf, ws.wbuf, ws.part, n, ldn};
+  APV_TRY(ensure_smem(td_gemv_kernel, (size_t)n * sizeof(double)));
+  int Gprev = 1;
+  for (int k0 = 0; k0 < n; k0 += NBT) {
+    const int pw = std::min(NBT, n - k0);
+    for (int jj = 0; jj < pw; ++jj) {
+      const int j = k0 + jj;
+      const int Gc = std::max(1, std::min(GMAX, ceil_div(n - j, 8)));
+      td_col_kernel<<<dim3(Gc, nz), 256, 0, st>>>(ta, j, jj, Gprev, 0);
+      ++nl;
+      if (j <= n - 2) {
+        const int G = std::max(1, std::min(GMAX, ceil_div(n - j - 1, 8)));
+        td_gemv_kernel<<<dim3(G, nz), 256, (size_t)(n - j - 1) * sizeof(double), st>>>(ta, j, jj, Gc);
+        td_w_kernel<<<dim3(G, nz), 256, 0, st>>>(ta, j, jj);
+        Gprev = G;
+        nl += 2;
+      }
+    }
+    const int r = k0 + pw;
+    if (r < n) {
+      // finalise the last w of the panel for rows >= r, then A22 -= V W^T + W V^T
+      const int Gc = std::max(1, std::min(GMAX, ceil_div(n - r, 8)));
+      td_col_kernel<<<dim3(Gc, nz), 256, 0, st>>>(ta, r, pw, Gprev, 1);
+      ++nl;
+      GemmArgs u{};
+      u.batch = nz;
+      u.A = ws.Z1 + (size_t)r * 2 * NBT; u.lda = 2 * NBT; u.strideA = (long long)n * 2 * NBT;
+      u.B = ws.Z2 + (size_t)r * 2 * NBT; u.ldb = 2 * NBT; u.strideB = (long long)n * 2 * NBT;
+      u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
+      u.M = n - r; u.N = n - r; u.K = 2 * NBT; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+      APV_TRY(gemm_f64(u, st));
+      ++nl;
+    }
+  }
+
+  // ---- top-V eigenpairs of T
+  double* tnorm = ws.shift + (size_t)nz * V;
+  APV_TRY(ensure_smem(eig_bisect_kernel, (size_t)2 * n * sizeof(double)));
+  eig_bisect_kernel<<<dim3(ceil_div(V, 8), nz), 256, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
+  eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
+  eig_invit_kernel<<<dim3(ws.Vp / 32, nz), 32, 0, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
+  eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
+  APV_TRY(ensure_smem(eig_backtransform_kernel, (size_t)n * sizeof(double)));
+  eig_backtransform_kernel<<<dim3(V, nz), 256, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.tau, ws.Zt, n, ldn, V, ws.Vp);
+  APV_TRY(ensure_smem(eig_backsolve_kernel, (size_t)n * sizeof(double)));
+  eig_backsolve_kernel<<<dim3(V, nz), 256, (size_t)n * sizeof(double), st>>>(ws.Lm, ws.Zt, n, ldn, V);
+  nl += 6;
+  APV_CUDA_TRY(cudaGetLastError());
+  if (launches) *launches += nl;
+  return OK;
+}
+
+}  // namespace apv

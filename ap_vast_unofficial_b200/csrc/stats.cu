@@ -1,0 +1,214 @@
+// S4  stats_syrk -- spatial statistics R_XY = sum_m Y_m Y_m^T (n x n) and r_X = sum_m Y_m d_m
+// (reference update_statistics / reset_statistics, Python/apvast.py:329-376; the data matrix of
+// apvast.py:334-338 is a block-Toeplitz matrix built with scipy.linalg.toeplitz).
+//
+// The n x P data matrix Y is never materialised.  With s' = delete(S[:, l, m], J) (SciPy's toeplitz
+// ignores r[0]) row (l, i) of Y is the window s'[J-1-i .. J-1-i+P) of ONE 1-D
+// signal, so a 128-row tile of Y over a chunk of KC columns is covered by (J + KC - 1) contiguous
+// samples per loudspeaker.  Those segments are staged in shared memory with cp.async (double
+// buffered) and the FP64 tensor-core fragments (mma.sync m8n8k4 = SASS DMMA.8x8x4) are gathered
+// from them by index arithmetic: A[row][k] = seg[(J-1-i) + k].  Only lower-triangle tiles are
+// computed; the epilogue mirrors them so R is stored as a full symmetric matrix.
+#include "engine.cuh"
+
+namespace apv {
+
+namespace {
+
+constexpr int TM = 128;      // CTA tile (rows = cols)
+constexpr int KC = 64;       // K chunk per pipeline stage
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
+
+// s'[e] = S[e < J ? e : e + 1], zero padded to Ns.  grid (4*M*L), one CTA per channel.
+__global__ void pack_stats_kernel(const double* __restrict__ S, double* __restrict__ Sp, int N, int J, int Ns) {
+  const double* s = S + (size_t)blockIdx.x * N;
+  double* sp = Sp + (size_t)blockIdx.x * Ns;
+  for (int e = threadIdx.x; e < Ns; e += blockDim.x) sp[e] = (e < N - 1) ? s[e < J ? e : e + 1] : 0.0;
+}
+
+// Tile list: lower-triangle tiles (bi >= bj) enumerated linearly; blockIdx.y = path.
+// Shared memory per stage: for the row side  nlr segments of SEG doubles, for the column side nlc segments,
+// plus one zero segment used by out-of-range rows.
+__global__ void __launch_bounds__(256, 1)
+syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ R, Dims D, int ntile, int SEG, int maxl,
+                     unsigned path_mask) {
+  const int path = blockIdx.y;
+  if (!((path_mask >> path) & 1u)) return;
+  // decode linear lower-triangle tile index -> (bi, bj), bi >= bj
+  int t = blockIdx.x, bi = 0;
+  while (t >= bi + 1) { t -= bi + 1; ++bi; }
+  const int bj = t;
+  const int r0 = bi * TM, c0 = bj * TM;
+  const int n = D.n, J = D.J, L = D.L, P = D.P;
+
+  extern __shared__ __align__(16) double sm[];
+  // stage layout: [row segs: maxl*SEG][col segs: maxl*SEG], two stages, then zero segment
+  const int stage_sz = 2 * maxl * SEG;
+  double* zero_seg = sm + 2 * stage_sz;
+  for (int i = threadIdx.x; i < SEG; i += blockDim.x) zero_seg[i] = 0.0;
+
+  const int lr0 = r0 / J, lr1 = min(L - 1, (r0 + TM - 1) / J);
+  const int lc0 = c0 / J, lc1 = min(L - 1, (c0 + TM - 1) / J);
+  const int nlr = lr1 - lr0 + 1, nlc = lc1 - lc0 + 1;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  // per-thread fragment base offsets (in doubles, relative to a stage base); negative = zero segment
+  int offA[8], offB[4];
+#pragma unroll
+  for (int rt = 0; rt < 8; ++rt) {
+    const int r = r0 + wm + rt * 8 + gq;
+    if (r < n) {
+      const int l = r / J, i = r - l * J;
+      offA[rt] = (l - lr0) * SEG + (J - 1 - i) + tq;
+    } else offA[rt] = -1;
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    const int c = c0 + wn + ct * 8 + gq;
+    if (c < n) {
+      const int l = c / J, i = c - l * J;
+      offB[ct] = maxl * SEG + (l - lc0) * SEG + (J - 1 - i) + tq;
+    } else offB[ct] = -1;
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nchunk = (P + KC - 1) / KC;
+  const int nit = D.M * nchunk;
+  const size_t chan_stride = (size_t)D.Ns;
+  const double* base = Sp + (size_t)path * D.M * L * chan_stride;
+
+  auto stage_load = [&](int it, int s) {
+    const int m = it / nchunk, p0 = (it - m * nchunk) * KC;
+    double* dst = sm + s * stage_sz;
+    const double* src = base + (size_t)m * L * chan_stride + p0;
+    const int tot_r = nlr * SEG;
+    for (int e = tid; e < tot_r; e += 256) {
+      const int ls = e / SEG, o = e - ls * SEG;
+      cp_async8(dst + e, src + (size_t)(lr0 + ls) * chan_stride + o);
+    }
+    const int tot_c = nlc * SEG;
+    for (int e = tid; e < tot_c; e += 256) {
+      const int ls = e / SEG, o = e - ls * SEG;
+      cp_async8(dst + maxl * SEG + e, src + (size_t)(lc0 + ls) * chan_stride + o);
+    }
+    cp_async_commit();
+  };
+
+  stage_load(0, 0);
+  for (int it = 0; it < nit; ++it) {
+    const int s = it & 1;
+    cp_async_wait_all();
+    __syncthreads();                      // stage s visible; everyone finished reading stage s^1
+    if (it + 1 < nit) stage_load(it + 1, s ^ 1);
+    const double* st = sm + s * stage_sz;
+    const int p0 = (it % nchunk) * KC;
+    const int klen = min(KC, P - p0);
+    const int nk4 = (klen + 3) >> 2;
+    const double* pa[8];
+    const double* pb[4];
+#pragma unroll
+    for (int rt = 0; rt < 8; ++rt) pa[rt] = offA[rt] >= 0 ? st + offA[rt] : zero_seg;
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) pb[ct] = offB[ct] >= 0 ? st + offB[ct] : zero_seg;
+    for (int kk = 0; kk < nk4; ++kk) {
+      const bool live = (kk * 4 + tq) < klen;      // mask the K tail on the A operand
+      double a[8], b[4];
+#pragma unroll
+      for (int rt = 0; rt < 8; ++rt) a[rt] = live ? pa[rt][kk * 4] : 0.0;
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) b[ct] = pb[ct][kk * 4];
+#pragma unroll
+      for (int rt = 0; rt < 8; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
+    }
+  }
+
+  double* Rp = R + (size_t)path * n * D.ldn;
+#pragma unroll
+  for (int rt = 0; rt < 8; ++rt) {
+    const int r = r0 + wm + rt * 8 + gq;
+    if (r >= n) continue;
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + wn + ct * 8 + 2 * tq + u;
+        if (c >= n) continue;
+        const double v = acc[rt][ct][u];
+        if (bi != bj) {
+          Rp[(size_t)r * D.ldn + c] = v;
+          Rp[(size_t)c * D.ldn + r] = v;
+        } else if (r >= c) {          // diagonal tile: keep the lower half and mirror it (exactly symmetric)
+          Rp[(size_t)r * D.ldn + c] = v;
+          Rp[(size_t)c * D.ldn + r] = v;
+        }
+      }
+    }
+  }
+}
+
+// r_X[(l,i)] = sum_m sum_p s'_{XX,l,m}[J-1-i+p] * ST_X[J+p, m].   grid (n/8 rows-of-8, 2 zones); warp per row.
+__global__ void __launch_bounds__(256) rvec_kernel(const double* __restrict__ Sp, const double* __restrict__ ST,
+                                                   double* __restrict__ rvec, Dims D, unsigned zone_mask) {
+  const int X = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= D.n) return;
+  if (!((zone_mask >> X) & 1u)) return;
+  const int path = X * 3;      // A->A = 0, B->B = 3
+  const int l = r / D.J, i = r - l * D.J;
+  double acc = 0.0;
+  for (int m = 0; m < D.M; ++m) {
+    const double* sp = Sp + (((size_t)path * D.M + m) * D.L + l) * D.Ns + (D.J - 1 - i);
+    const double* dm = ST + ((size_t)X * D.M + m) * D.N + D.J;
+    double a = 0.0;
+    for (int p = lane; p < D.P; p += 32) a = fma(sp[p], dm[p], a);
+    acc += warp_sum(a);
+  }
+  if (lane == 0) rvec[(size_t)X * D.n + r] = acc;
+}
+
+}  // namespace
+
+int stage_stats(Handle& h) {
+  const Dims& D = h.D;
+  pack_stats_kernel<<<4 * D.M * D.L, 256, 0, h.st>>>(h.S, h.Sp, D.N, D.J, D.Ns);
+  const int nt = ceil_div(D.n, TM);
+  const int ntile = nt * (nt + 1) / 2;
+  const int SEG = round_up(D.J + KC - 1, 2);
+  const int maxl = min(D.L, (TM - 1) / D.J + 2);
+  const size_t sm = (size_t)(4 * maxl * SEG + SEG) * sizeof(double);
+  if (sm > 220 * 1024) {
+    snprintf(g_err, sizeof(g_err), "stats_syrk: filter_length %d too small for the tile staging (%zu B smem)", D.J, sm);
+    return EINVAL_;
+  }
+  static thread_local size_t configured = 0;
+  if (sm > configured) {
+    APV_CUDA_TRY(cudaFuncSetAttribute(syrk_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    configured = sm;
+  }
+  unsigned pmask = (D.runA ? 0x3u : 0u) | (D.runB ? 0xCu : 0u);
+  unsigned zmask = (D.runA ? 1u : 0u) | (D.runB ? 2u : 0u);
+  syrk_toeplitz_kernel<<<dim3(ntile, 4), 256, sm, h.st>>>(h.Sp, h.R, D, ntile, SEG, maxl, pmask);
+  rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
+  h.launches += 3;
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
+}  // namespace apv

@@ -1,0 +1,163 @@
+/*
+ * apvast_b200.h -- C-ABI of the B200-native AP-VAST block engine.
+ *
+ * Drop-in boundary for the hot path of macoustics/ap-vast-unofficial: the Python class `apvast`
+ * (reference Python/apvast.py:39) -- constructor (:40-151) and per-block call
+ * `process_input_buffers(input_A, input_B)` (:153-165) -- and the `jdiag` it calls (:20-36).
+ * The reference has no FFI of its own (it is pure NumPy/SciPy); these entry points are what a
+ * ctypes binding for that path binds (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; all arithmetic is IEEE float64; all host arrays are C-order.
+ *   - every function returns 0 (APV_OK) or a positive status; apv_last_error() gives the message.
+ *   - one handle = one ordered stream of hops (like one reference object); calls on a handle are
+ *     serialised by the caller.  One CUDA stream per handle.
+ *   - no cuBLAS / cuSOLVER / cuFFT symbols are linked; there is no CPU fallback.
+ */
+#ifndef APVAST_B200_H
+#define APVAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum apv_status {
+  APV_OK = 0,
+  APV_EINVAL = 1,  /* bad argument / size (reference raises RuntimeError, apvast.py:86-90,154-155) */
+  APV_ENOTPD = 2,  /* R_D + reg*I not positive definite (reference: numpy LinAlgError, apvast.py:21-24) */
+  APV_ECUDA = 3,   /* CUDA runtime error */
+  APV_ENOMEM = 4,
+  APV_ENOCONV = 5  /* eigen-solver did not converge */
+};
+
+/* Constructor parameters: reference apvast.__init__ (apvast.py:40-56) + module flags (:6-7). */
+typedef struct apv_config {
+  int32_t block_size;        /* Nb, even                          (ctor block_size, :41)            */
+  int32_t hop_size;          /* H, 0 -> Nb/2                      (ctor hop_size, :51,93)           */
+  int32_t rir_length;        /* K = rir.shape[0]                  (:97)                             */
+  int32_t n_srcs;            /* L = rir.shape[1]                  (:98)                             */
+  int32_t n_mics;            /* M = rir.shape[2]                  (:99)                             */
+  int32_t filter_length;     /* J                                 (:44)                             */
+  int32_t stats_length;      /* N = statistics_buffer_length      (:50)                             */
+  int32_t n_eig;             /* V = number_of_eigenvectors        (:48)                             */
+  int32_t modeling_delay;    /* d                                 (:45)                             */
+  int32_t ref_A, ref_B;      /* reference_index_A/B, 0-based      (:46-47)                          */
+  int32_t run_A, run_B;      /* (:53-54)                                                            */
+  int32_t perceptual;        /* 0: W == 1 (:326-327); 1: on-device masking model (apv_set_gain_table);
+                                2: weighting spectra supplied by the host per block (apv_set_weights) */
+  int32_t normalize_gains;   /* EXPERIMENTAL_NORMALIZE_GAINS (:6,322-324)                           */
+  int32_t eig_mode;          /* 0 auto; 1 tridiagonal + bisection + inverse iteration (top-V);
+                                2 cyclic Jacobi (small n, full spectrum)                            */
+  int32_t stats_mode;        /* 0 auto; 1 FP64 tensor-core SYRK with implicit Toeplitz operand      */
+  int32_t device;            /* CUDA device ordinal, -1 = current                                   */
+  double mu;                 /* (:49)                                                               */
+  double reg;                /* absolute diagonal loading inside jdiag, reference 1e-7 (:22-24)     */
+  double sampling_rate;      /* (:52)                                                               */
+} apv_config;
+
+typedef struct apv_handle apv_handle;
+
+/* Tensor ids for apv_get / apv_set.  Device layouts are channel-major, time-contiguous;
+ * the Python host transposes to the reference's attribute shapes. */
+enum apv_tensor {
+  APV_T_W = 0,            /* [zone 2][V][n]                 filters w_A, w_B (apvast.py:393-414)            */
+  APV_T_LAMBDA = 1,       /* [zone 2][V]                    top-V eigenvalues, descending (:385-387)        */
+  APV_T_U = 2,            /* [zone 2][V][n]                 top-V joint eigenvectors, row v = U[:, v]       */
+  APV_T_R = 3,            /* [path 4][n][n]                 R_A_to_A, R_A_to_B, R_B_to_A, R_B_to_B (:368-372)*/
+  APV_T_RVEC = 4,         /* [zone 2][n]                    r_A, r_B (:373-376)                             */
+  APV_T_WEIGHT = 5,       /* [zone 2][M][F]                 real weighting gains W_A, W_B (:315-327)        */
+  APV_T_RESP = 6,         /* [path 4][M][L][Nb]             loudspeaker_response_*_buffer (:124-127)        */
+  APV_T_RESP_T = 7,       /* [zone 2][M][Nb]                loudspeaker_target_response_*_buffer (:128-129) */
+  APV_T_OLA = 8,          /* [path 4][M][L][Nb]             ..._weighted_response_*_overlap_buffer (:132-135)*/
+  APV_T_OLA_T = 9,        /* [zone 2][M][Nb]                ..._weighted_target_*_overlap_buffer (:136-137) */
+  APV_T_STATS = 10,       /* [path 4][M][L][N]              ..._weighted_response_*_buffer (:140-143)       */
+  APV_T_STATS_T = 11,     /* [zone 2][M][N]                 ..._weighted_target_response_*_buffer (:144-145)*/
+  APV_T_OUT_OLA = 12,     /* [zone 2][V][L][Nb]             output_A/B_overlap_buffer (:148-149)            */
+  APV_T_OUT_OLA_T = 13,   /* [zone 2][Nb]                   output_*_t_overlap_buffer, reference loudspeaker
+                                                            column (all other columns are zero, :150-151)   */
+  APV_T_INPUT = 14,       /* [signal 2][LX]                 most recent input samples, newest last;
+                                                            LX = max(K-1, Nb) (input_*_block + FIR history) */
+  APV_T_TARGET_FRAME = 15 /* [zone 2][M][Nb]                irfft of the windowed target spectra: what the
+                                                            reference passes to model.gain (:318-319)       */
+};
+
+/* Element count of a tensor (0 if unknown id). */
+size_t apv_tensor_size(const apv_handle* h, int tensor_id);
+
+/* Constructor.  rir_A/rir_B: (K, L, M) C-order (apvast.py:42-43).  init_resp: the six 1e-3*randn start
+ * buffers in the reference draw order (:124-129): 4 x (Nb, L, M) then 2 x (Nb, M), C-order, concatenated;
+ * NULL = zeros. */
+int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, const double* init_resp,
+               apv_handle** out);
+void apv_destroy(apv_handle* h);
+
+/* One filter update = reference process_input_buffers (apvast.py:153-165).  in_A/in_B: H samples (host).
+ * out_A/out_B: (V, H, L) C-order host buffers or NULL; out_A_t/out_B_t: (H, L) C-order host buffers or
+ * NULL (the reference returns V identical copies of these, :418,422,467-475). */
+int apv_process_block(apv_handle* h, const double* in_A, const double* in_B, double* out_A, double* out_B,
+                      double* out_A_t, double* out_B_t);
+
+/* Throughput path: nblocks consecutive hops in one call; identical results.  in_*: (nblocks, H);
+ * out_A/out_B: (nblocks, V, H, L) or NULL; out_*_t: (nblocks, H, L) or NULL;
+ * w_out: (nblocks, 2, V, n) or NULL (per-block filters). */
+int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const double* in_B, double* out_A,
+                       double* out_B, double* out_A_t, double* out_B_t, double* w_out);
+
+/* Same as apv_process_block but inputs/outputs are DEVICE pointers and nothing is copied or synchronised
+ * (used to time the kernels with inputs resident in HBM). */
+int apv_process_block_device(apv_handle* h, const double* d_in_A, const double* d_in_B);
+
+/* Split call for perceptual == 2 (host gain model, e.g. libdetectability, apvast.py:318-319):
+ * begin = S1 + target spectra; read APV_T_TARGET_FRAME; set APV_T_WEIGHT; finish = S2..S7. */
+int apv_begin_block(apv_handle* h, const double* in_A, const double* in_B);
+int apv_finish_block(apv_handle* h, double* out_A, double* out_B, double* out_A_t, double* out_B_t);
+
+/* Warm-up only: S1-S3 (state update) without statistics / filters / rendering (multi-GPU halo). */
+int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B);
+
+int apv_get(apv_handle* h, int tensor_id, double* dst, size_t count);
+int apv_set(apv_handle* h, int tensor_id, const double* src, size_t count);
+int apv_set_mu(apv_handle* h, double mu);
+
+/* Perceptual masking model tables (perceptual == 1): G2[c][f] = (outer/middle-ear x gammatone)^2,
+ * C channels x F = Nb/2+1 bins, and the calibration constants (perceptualModel.m:30-139). */
+int apv_set_gain_table(apv_handle* h, int n_channels, const double* G2, double Cs, double Ca, double Leff);
+
+/* mu x V trade-off sweep (BASELINE cfg-4): filters for n_mu values of mu from ONE joint diagonalisation.
+ * w_out: (n_mu, 2, V, n) host buffer. */
+int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out);
+
+/* Device pointer of a tensor (for torch.distributed / NCCL plumbing on the caller's side). */
+int apv_device_ptr(apv_handle* h, int tensor_id, void** ptr);
+int apv_synchronize(apv_handle* h);
+
+/* Per-stage device time of the last apv_process_block* call, milliseconds:
+ * [0] S1 rir_conv [1] S2+S3 wola_weight [2] S4 stats [3] S5 jdiag [4] S6 sweep [5] S7 render [6] total. */
+int apv_stage_times(apv_handle* h, float* ms7);
+/* Number of kernel launches issued by the last apv_process_block* call. */
+int apv_launch_count(const apv_handle* h);
+
+/* Stand-alone joint diagonalisation = reference jdiag(A, B) (apvast.py:20-36), top-V pairs.
+ * A, B: (n, n) host; lambda_out: (V); U_out: (V, n) row v = U[:, v].  pivot_out: first bad pivot if ENOTPD. */
+int apv_jdiag(int n, int V, const double* A, const double* B, double reg, int eig_mode, double* lambda_out,
+              double* U_out, int* pivot_out);
+
+/* Test / measurement utilities. */
+int apv_util_gemm(int M, int N, int K, int transA, int transB, double alpha, const double* A, const double* B,
+                  double beta, double* C);
+int apv_util_fft(int n, int inverse, const double* in_ri, double* out_ri);
+/* FP64 DMMA issue-rate microbenchmark: returns achieved TFLOP/s. */
+int apv_bench_dmma_peak(int iters, double* tflops);
+/* Times nrep launches of the internal GEMM (M=N=K=n) on device data; returns ms per launch. */
+int apv_bench_gemm(int n, int nrep, float* ms);
+
+const char* apv_last_error(void);
+const char* apv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APVAST_B200_H */
