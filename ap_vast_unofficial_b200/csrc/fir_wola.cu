@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) fir_kernel(const double* __restrict__ xin
   for (int i = threadIdx.x; i < K - 1 + H; i += blockDim.x) xs[i] = xe[i];
   __syncthreads();
   // y[h] = sum_k rir[k] xe[K-1+h-k] = sum_j hs[j] xs[h+j]
+  double* ys = xs + (K - 1 + H);   // new samples, shared so that any thread can append them
   for (int i0 = threadIdx.x; i0 < H; i0 += 4 * blockDim.x) {
     double acc[4] = {0, 0, 0, 0};
     int hh[4];
@@ -110,10 +111,13 @@ __global__ void __launch_bounds__(256) fir_kernel(const double* __restrict__ xin
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * blockDim.x;
-      if (i < H)
-        for (int j = i; j < Nb; j += H) q[j] = (j + H < Nb) ? q[j + H] : acc[u];
+      if (i < H) ys[i] = acc[u];
     }
   }
+  __syncthreads();
+  // q <- [q[H:], y]: thread i owns the residue class {i, i+H, ...} and walks it upwards (in place)
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    for (int j = i; j < Nb; j += H) q[j] = (j + H < Nb) ? q[j + H] : ys[j + H - Nb];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -125,16 +129,14 @@ __device__ void wola_tail(double2* spec, double2* other, const double2* tw, cons
   double2* y = spec;
   if (!zero_frame) y = block_fft(spec, other, tw, Nb, pl.nrad, pl.rad, true);
   const double inv = 1.0 / Nb;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    double first = 0.0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
     for (int j = i; j < Nb; j += H) {
       const double fr = zero_frame ? 0.0 : win[j] * (y[j].x * inv);
-      const double v = ((j + H < Nb) ? ola[j + H] : 0.0) + fr;
-      ola[j] = v;
-      if (j == i) first = v;
+      ola[j] = ((j + H < Nb) ? ola[j + H] : 0.0) + fr;
     }
-    for (int j = i; j < N; j += H) stats[j] = (j + H < N) ? stats[j + H] : first;
-  }
+  __syncthreads();      // ola[0..H) complete (global writes of this CTA are visible after the barrier)
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    for (int j = i; j < N; j += H) stats[j] = (j + H < N) ? stats[j + H] : ola[j + H - N];
 }
 
 // Hermitian extension of a real gain curve g[0..F) to bin f in [0, Nb)
@@ -286,7 +288,7 @@ int fft_plan(int n, int* rad, int* nrad) {
 int stage_fir(Handle& h, const double* d_inA, const double* d_inB) {
   const Dims& D = h.D;
   input_shift_kernel<<<2, 256, 0, h.st>>>(h.xin, d_inA, d_inB, D.LX, D.H);
-  size_t sm = (size_t)(2 * D.K - 1 + D.H) * sizeof(double);
+  size_t sm = (size_t)(2 * D.K - 1 + 2 * D.H) * sizeof(double);
   APV_TRY(ensure_smem(fir_kernel, sm));
   fir_kernel<<<dim3(D.L, D.M, 6), 256, sm, h.st>>>(h.xin, h.rirT, h.rirTT, h.Q, h.QT, D);
   h.launches += 2;
