@@ -223,6 +223,10 @@ class apvast:
         keys = ("S1_rir_conv", "S2S3_wola_weight", "S4_stats", "S5_jdiag", "S6_sweep", "S7_render", "total")
         d = {k: float(ms[i]) for i, k in enumerate(keys)}
         d["launches"] = int(capi.lib().apv_launch_count(self._h))
+        ph = (C.c_float * 6)()
+        capi.check(capi.lib().apv_jdiag_phase_times(self._h, ph))
+        for i, k in enumerate(("chol", "reduce", "tridiag", "eig", "backtransform", "backsolve")):
+            d["S5_" + k] = float(ph[i])
         return d
 
     # ------------------------------------------------------------------ raw tensor access

@@ -479,6 +479,15 @@ int apv_stage_times(apv_handle* h, float* ms7) {
   return OK;
 }
 
+int apv_jdiag_phase_times(apv_handle* h, float* ms6) {
+  if (!h || !ms6) return fail(EINVAL_, "null argument");
+  for (int i = 0; i < 6; ++i) ms6[i] = 0.f;
+  if (h->nz == 0) return OK;
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms6[i], h->jd.ev[i], h->jd.ev[i + 1]);
+  return OK;
+}
+
 int apv_launch_count(const apv_handle* h) { return h ? h->launches : 0; }
 
 int apv_jdiag(int n, int V, const double* A, const double* B, double reg, int eig_mode, double* lambda_out,

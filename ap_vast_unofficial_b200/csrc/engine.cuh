@@ -30,7 +30,8 @@ struct JdiagWs {
   double* colbuf = nullptr; // [nz][n]
   double* ybuf = nullptr;   // [nz][n]
   double* wbuf = nullptr;   // [nz][n]
-  double* part = nullptr;   // [nz][PARTS][2 nbt + 2] per-CTA partial sums
+  double* part = nullptr;   // per-CTA partial sums of the panel kernel: [nz][GMAX] w.v + [nz][GMAX][2 nbt]
+  double* vcur = nullptr;   // [nz][2][n] current Householder vector (double buffered)
   double* lam = nullptr;    // [nz][V]   top-V eigenvalues, descending
   double* shift = nullptr;  // [nz][V]   perturbed shifts for inverse iteration
   double* iv = nullptr;     // [nz][6][n][Vp] inverse-iteration work (interleaved over vectors)
@@ -38,6 +39,7 @@ struct JdiagWs {
   int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
   int Vp = 0;
   size_t bytes = 0;
+  cudaEvent_t ev[8] = {};   // phase boundaries: prep | chol | reduce | tridiag | eig | backtransform | solve
 };
 int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode);
 void jdiag_free(JdiagWs& ws);

@@ -79,7 +79,7 @@ enum apv_tensor {
   APV_T_OUT_OLA_T = 13,   /* [zone 2][Nb]                   output_*_t_overlap_buffer, reference loudspeaker
                                                             column (all other columns are zero, :150-151)   */
   APV_T_INPUT = 14,       /* [signal 2][LX]                 most recent input samples, newest last;
-                                                            LX = max(K-1, Nb) (input_*_block + FIR history) */
+                                                            LX = max(K-1+H, Nb) (input_*_block + FIR history) */
   APV_T_TARGET_FRAME = 15 /* [zone 2][M][Nb]                irfft of the windowed target spectra: what the
                                                             reference passes to model.gain (:318-319)       */
 };
@@ -137,6 +137,10 @@ int apv_synchronize(apv_handle* h);
 /* Per-stage device time of the last apv_process_block* call, milliseconds:
  * [0] S1 rir_conv [1] S2+S3 wola_weight [2] S4 stats [3] S5 jdiag [4] S6 sweep [5] S7 render [6] total. */
 int apv_stage_times(apv_handle* h, float* ms7);
+/* Device time of the phases of the last joint diagonalisation (S5), milliseconds:
+ * [0] Cholesky [1] two-sided reduction C = L^-1 R_B L^-T [2] tridiagonalisation
+ * [3] bisection + inverse iteration [4] back-transformation [5] U = L^-T Q. */
+int apv_jdiag_phase_times(apv_handle* h, float* ms6);
 /* Number of kernel launches issued by the last apv_process_block* call. */
 int apv_launch_count(const apv_handle* h);
 
