@@ -56,6 +56,9 @@ SIGNATURES = {
     "apv_synchronize": (C.c_int, [C.c_void_p]),
     "apv_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "apv_jdiag_phase_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "apv_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "apv_timer_start": (C.c_int, [C.c_void_p]),
+    "apv_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "apv_launch_count": (C.c_int, [C.c_void_p]),
     "apv_jdiag": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
     "apv_util_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, _dp]),

@@ -229,6 +229,8 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
 #define CUB(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return bail(fail(ECUDA, "%s -> %s", #x, cudaGetErrorString(_e))); } while (0)
   CUB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   for (auto& e : h->ev) CUB(cudaEventCreate(&e));
+  for (auto& e : h->ev_syrk) CUB(cudaEventCreate(&e));
+  for (auto& e : h->ev_timer) CUB(cudaEventCreate(&e));
   const size_t K = D.K, L = D.L, M = D.M, Nb = D.Nb, N = D.N, V = D.V, n = D.n;
   TRYB(dalloc(&h->rirT, 2 * M * L * K));
   TRYB(dalloc(&h->rirTT, 2 * M * K));
@@ -322,6 +324,10 @@ void apv_destroy(apv_handle* h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   jdiag_free(h->jd);
   for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_syrk)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_timer)
     if (e) cudaEventDestroy(e);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
@@ -485,6 +491,39 @@ int apv_jdiag_phase_times(apv_handle* h, float* ms6) {
   if (h->nz == 0) return OK;
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms6[i], h->jd.ev[i], h->jd.ev[i + 1]);
+  return OK;
+}
+
+int apv_kernel_times(apv_handle* h, float* ms4) {
+  if (!h || !ms4) return fail(EINVAL_, "null argument");
+  for (int i = 0; i < 4; ++i) ms4[i] = 0.f;
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  if (h->nz > 0) {
+    cudaEventElapsedTime(&ms4[1], h->ev_syrk[0], h->ev_syrk[1]);
+    float tot = 0.f;
+    for (int p = 0; p < h->jd.npanel; ++p) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, h->jd.pev[2 * p], h->jd.pev[2 * p + 1]);
+      tot += t;
+    }
+    ms4[0] = tot;
+    ms4[2] = (float)h->jd.npanel;
+  }
+  return OK;
+}
+
+int apv_timer_start(apv_handle* h) {
+  if (!h) return fail(EINVAL_, "null argument");
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  APV_CUDA_TRY(cudaEventRecord(h->ev_timer[0], h->st));
+  return OK;
+}
+
+int apv_timer_stop(apv_handle* h, float* ms) {
+  if (!h || !ms) return fail(EINVAL_, "null argument");
+  APV_CUDA_TRY(cudaEventRecord(h->ev_timer[1], h->st));
+  APV_CUDA_TRY(cudaEventSynchronize(h->ev_timer[1]));
+  APV_CUDA_TRY(cudaEventElapsedTime(ms, h->ev_timer[0], h->ev_timer[1]));
   return OK;
 }
 

@@ -40,6 +40,8 @@ struct JdiagWs {
   int Vp = 0;
   size_t bytes = 0;
   cudaEvent_t ev[8] = {};   // phase boundaries: prep | chol | reduce | tridiag | eig | backtransform | solve
+  cudaEvent_t* pev = nullptr;   // [2 * npanel] events around every td_panel_kernel launch (roofline timing)
+  int npanel = 0;
 };
 int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode);
 void jdiag_free(JdiagWs& ws);
@@ -53,6 +55,8 @@ struct Handle {
   Dims D;
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_syrk[2] = {};   // around the statistics SYRK kernel
+  cudaEvent_t ev_timer[2] = {};  // apv_timer_start / apv_timer_stop
   int device = 0;
   // constants
   double* rirT = nullptr;    // [zone 2][M][L][K]

@@ -803,6 +803,9 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.Zt, (size_t)nz * V * n * sizeof(double)));
   APV_TRY(al((void**)&ws.info, (size_t)nz * 4 * sizeof(int)));
   for (auto& e : ws.ev) APV_CUDA_TRY(cudaEventCreate(&e));
+  ws.npanel = ceil_div(n, NBT);
+  ws.pev = new cudaEvent_t[2 * ws.npanel]();
+  for (int i = 0; i < 2 * ws.npanel; ++i) APV_CUDA_TRY(cudaEventCreate(&ws.pev[i]));
   ws.bytes = total;
   return OK;
 }
@@ -814,6 +817,11 @@ void jdiag_free(JdiagWs& ws) {
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
     if (e) cudaEventDestroy(e);
+  if (ws.pev) {
+    for (int i = 0; i < 2 * ws.npanel; ++i)
+      if (ws.pev[i]) cudaEventDestroy(ws.pev[i]);
+    delete[] ws.pev;
+  }
   ws = JdiagWs();
 }
 
@@ -911,7 +919,9 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
       int pw = std::min(NBT, n - k0);
       int k0v = k0;
       void* args[] = {(void*)&tp, (void*)&k0v, (void*)&pw};
+      APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT)], st));
       APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)td_panel_kernel, dim3(G * nz), dim3(TDT), args, tdsm, st));
+      APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT) + 1], st));
       ++nl;
       const int r = k0 + pw;
       if (r < n) {         // A22 -= V W^T + W V^T

@@ -204,7 +204,9 @@ int stage_stats(Handle& h) {
   }
   unsigned pmask = (D.runA ? 0x3u : 0u) | (D.runB ? 0xCu : 0u);
   unsigned zmask = (D.runA ? 1u : 0u) | (D.runB ? 2u : 0u);
+  APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[0], h.st));
   syrk_toeplitz_kernel<<<dim3(ntile, 4), 256, sm, h.st>>>(h.Sp, h.R, D, ntile, SEG, maxl, pmask);
+  APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
   rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
   h.launches += 3;
   APV_CUDA_TRY(cudaGetLastError());

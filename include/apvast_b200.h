@@ -141,6 +141,13 @@ int apv_stage_times(apv_handle* h, float* ms7);
  * [0] Cholesky [1] two-sided reduction C = L^-1 R_B L^-T [2] tridiagonalisation
  * [3] bisection + inverse iteration [4] back-transformation [5] U = L^-T Q. */
 int apv_jdiag_phase_times(apv_handle* h, float* ms6);
+/* Device time of the two dominant kernels in the last block, milliseconds: [0] sum over all td_panel_kernel
+ * launches (tridiagonalisation, HBM/L2 bound) [1] syrk_toeplitz_kernel (statistics, FP64 tensor bound)
+ * [2] number of td_panel_kernel launches [3] reserved. */
+int apv_kernel_times(apv_handle* h, float* ms4);
+/* CUDA-event timer on the handle's stream (the stream every kernel of the handle is launched on). */
+int apv_timer_start(apv_handle* h);
+int apv_timer_stop(apv_handle* h, float* ms);
 /* Number of kernel launches issued by the last apv_process_block* call. */
 int apv_launch_count(const apv_handle* h);
 
