@@ -30,7 +30,7 @@ struct JdiagWs {
   double* colbuf = nullptr; // [nz][n]
   double* ybuf = nullptr;   // [nz][n]
   double* wbuf = nullptr;   // [nz][n]
-  double* part = nullptr;   // per-CTA partial sums of the panel kernel: [nz][GMAX] w.v + [nz][GMAX][2 nbt]
+  double* tdws = nullptr;   // scratch of the tridiagonalisation panel kernel (partials, tile partial vectors)
   double* vcur = nullptr;   // [nz][2][n] current Householder vector (double buffered)
   double* lam = nullptr;    // [nz][V]   top-V eigenvalues, descending
   double* shift = nullptr;  // [nz][V]   perturbed shifts for inverse iteration
@@ -46,6 +46,9 @@ struct JdiagWs {
 int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode);
 void jdiag_free(JdiagWs& ws);
 // bright[z], dark[z]: device n x n matrices with leading dimension ld_in.
+// tridiag.cu: Cm -> (dd, ee, VH, tau); uses Z1/Z2/colbuf/tdws.  Adds its kernel launches to *launches.
+int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches);
+size_t tridiag_scratch_doubles(int n, int nz);
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
               cudaStream_t st, int* launches);
 

@@ -12,14 +12,11 @@
 // Both zone problems are batched in every launch (blockIdx.y / blockIdx.z = zone).
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
-#include <cooperative_groups.h>
-
 #include "engine.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace apv {
 
@@ -27,7 +24,6 @@ namespace {
 
 constexpr int NB = 64;    // Cholesky / TRSM block size
 constexpr int NBT = 32;   // tridiagonalisation panel width (one V and one W column per lane)
-constexpr int GMAX = 256; // upper bound of CTAs per zone in the panel kernel
 
 struct Ptr2 {
   const double* p[2];
@@ -127,280 +123,6 @@ __global__ void symmetrize_kernel(const double* __restrict__ in, double* __restr
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = by + r, j = bx + threadIdx.x;
     if (i < n && j < n) out[zo + (size_t)i * ldn + j] = 0.5 * (in[zo + (size_t)i * ldn + j] + t[threadIdx.x][r]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Blocked Householder tridiagonalisation (lower variant of LAPACK dsytrd/dlatrd, full symmetric storage).
-// Panel storage: Z1[i][0..NBT) = V, Z1[i][NBT..2NBT) = W;  Z2[i][0..NBT) = W, Z2[i][NBT..2NBT) = V, so that the
-// trailing update A22 -= V W^T + W V^T is one DMMA GEMM  A22 -= Z1 Z2^T  with K = 2 NBT.
-// (kernel) One persistent cooperative kernel per panel of NBT columns, 2 grid barriers per column.
-//
-//   phase P1(j): (jj > 0) raw w of the previous column,  w = tau (y - V (W^T v) - W (V^T v)),  its
-//                partial w.v, and the updated column j as a function of the still unknown
-//                gamma = tau/2 (w.v):   x = a + 2 gamma v_prev   (a goes to colbuf)
-//   --- grid barrier ---
-//   phase P2(j): gamma, x and the reflector (beta, tau, v) -- every CTA redundantly, it needs all
-//                of v for its GEMV rows anyway --, final W column of the previous reflector,
-//                y = A[j+1:, j+1:] v for the CTA's rows (the HBM/L2-bound part: 4 x 16-byte loads in
-//                flight per lane, 16 warps per SM), partial (panel)^T v
-//   --- grid barrier ---
-// CTAs are split between the zone problems (zone = blockIdx.x % nz).  Everything another CTA wrote
-// during the kernel is read with ld.global.cg (L2), never through the non-coherent L1.
-struct TdPanel {
-  double* Cm; double* VH; double* Z1; double* Z2; double* tau; double* dd; double* ee;
-  double* colbuf; double* ybuf; double* wbuf;
-  double* vcur;   // [nz][2][n]        current reflector, double buffered by column parity
-  double* pwv;    // [nz][G]           partial w.v
-  double* tpart;  // [nz][G][2 NBT]    partial (panel col)^T v
-  int n, ldn, nz;
-};
-
-constexpr int TDT = 512;        // threads per CTA of the panel kernel
-constexpr int TDW = TDT / 32;
-constexpr int TD_TS = 0, TD_TRED = 2 * NBT, TD_RED = TD_TRED + 8 * 2 * NBT, TD_SC = TD_RED + 40, TD_EXTRA = TD_SC + 8;
-
-__device__ __forceinline__ void chunk_of(int lo, int hi, int G, int g, int& a, int& b) {
-  const int rows = hi - lo, per = (rows + G - 1) / G;
-  a = lo + g * per;
-  b = min(hi, a + per);
-}
-
-__device__ __forceinline__ double td_gamma(const TdPanel& a, double* ex, int z, int G, int j, int jj) {
-  if (jj == 0) return 0.0;
-  if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (int q = threadIdx.x; q < G; q += 32) s += __ldcg(a.pwv + (size_t)z * G + q);
-    s = warp_sum(s);
-    if (threadIdx.x == 0) ex[TD_SC] = 0.5 * __ldcg(a.tau + (size_t)z * a.n + j - 1) * s;
-  }
-  __syncthreads();
-  return ex[TD_SC];
-}
-
-__device__ __forceinline__ void td_phase1(const TdPanel& a, double* ex, int z, int g, int G, int j, int jj,
-                                          bool w_only) {
-  const int n = a.n, ldn = a.ldn;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* ts = ex + TD_TS;
-  double* tred = ex + TD_TRED;
-  double* red = ex + TD_RED;
-  const double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
-  const double* Cm = a.Cm + (size_t)z * n * ldn;
-  double* colbuf = a.colbuf + (size_t)z * n;
-  double* wbuf = a.wbuf + (size_t)z * n;
-  const double* ybuf = a.ybuf + (size_t)z * n;
-  const double* vprev = a.vcur + ((size_t)z * 2 + ((jj + 1) & 1)) * n;   // written in P2 of column j-1
-  int r0, r1;
-  chunk_of(j, n, G, g, r0, r1);
-  if (jj == 0) {
-    for (int i = r0 + threadIdx.x; i < r1; i += TDT) colbuf[i] = Cm[(size_t)j * ldn + i];
-    return;
-  }
-  {  // reduce the partial panel^T v of column j-1 (columns c' < jj-1 of V and of W)
-    const int col = threadIdx.x & 63, qg = threadIdx.x >> 6;       // 8 groups of 64
-    double s = 0.0;
-    if ((col & (NBT - 1)) < jj - 1) {
-      const double* tp = a.tpart + (size_t)z * G * 2 * NBT;
-      for (int q = qg; q < G; q += 8) s += __ldcg(tp + (size_t)q * 2 * NBT + col);
-    }
-    tred[qg * 2 * NBT + col] = s;
-    __syncthreads();
-    if (threadIdx.x < 2 * NBT) {
-      double t = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += tred[q * 2 * NBT + threadIdx.x];
-      ts[threadIdx.x] = t;
-    }
-    __syncthreads();
-  }
-  const double tau_p = __ldcg(a.tau + (size_t)z * n + j - 1);
-  const int nc = jj - 1;                       // finished panel columns
-  // lane c' holds V[j][c'], W[j][c'] and the reduced dots; every CTA recomputes the raw w of row j
-  double Vj = 0.0, Wj = 0.0, tW = 0.0, tV = 0.0;
-  if (lane < nc) {
-    Vj = __ldcg(Z1 + (size_t)j * 2 * NBT + lane);
-    Wj = __ldcg(Z1 + (size_t)j * 2 * NBT + NBT + lane);
-    tW = ts[NBT + lane];
-    tV = ts[lane];
-  }
-  const double wj = tau_p * (__ldcg(ybuf + j) - warp_sum(Vj * tW + Wj * tV));
-  double wv = 0.0;
-  for (int i = r0 + warp; i < r1; i += TDW) {
-    double cw = 0.0, cx = 0.0;
-    if (lane < nc) {
-      const double Vi = __ldcg(Z1 + (size_t)i * 2 * NBT + lane), Wi = __ldcg(Z1 + (size_t)i * 2 * NBT + NBT + lane);
-      cw = Vi * tW + Wi * tV;
-      cx = Vi * Wj + Wi * Vj;
-    }
-    cw = warp_sum(cw);
-    cx = warp_sum(cx);
-    if (lane == 0) {
-      const double wi = tau_p * (__ldcg(ybuf + i) - cw);
-      const double vi = __ldcg(vprev + i);
-      wbuf[i] = wi;
-      wv += wi * vi;
-      if (!w_only) colbuf[i] = Cm[(size_t)j * ldn + i] - cx - vi * wj - wi;   // uses V[j][jj-1] = 1
-    }
-  }
-  if (lane == 0) red[warp] = wv;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < TDW; ++w) s += red[w];
-    a.pwv[(size_t)z * G + g] = s;
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void td_phase2(const TdPanel& a, double* xs, double* ex, int z, int g, int G, int j,
-                                          int jj) {
-  const int n = a.n, ldn = a.ldn;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* tred = ex + TD_TRED;
-  double* red = ex + TD_RED;
-  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
-  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
-  const double* Cm = a.Cm + (size_t)z * n * ldn;
-  const double* colbuf = a.colbuf + (size_t)z * n;
-  const double* wbuf = a.wbuf + (size_t)z * n;
-  double* ybuf = a.ybuf + (size_t)z * n;
-  const double* vprev = a.vcur + ((size_t)z * 2 + ((jj + 1) & 1)) * n;
-  double* vnew = a.vcur + ((size_t)z * 2 + (jj & 1)) * n;
-  const double gamma = td_gamma(a, ex, z, G, j, jj);
-  // x = a + 2 gamma v_prev for all rows >= j (absolute index in xs)
-  double ss = 0.0;
-  for (int i = j + threadIdx.x; i < n; i += TDT) {
-    double x = __ldcg(colbuf + i);
-    if (jj > 0) x = fma(2.0 * gamma, __ldcg(vprev + i), x);
-    xs[i] = x;
-    if (i >= j + 2) ss = fma(x, x, ss);
-  }
-  ss = block_sum(ss, red);
-  const double dj = xs[j];
-  if (j == n - 1) {
-    if (g == 0 && threadIdx.x == 0) a.dd[(size_t)z * n + j] = dj;
-    return;
-  }
-  const double alpha = xs[j + 1];
-  double beta, tau, scal;
-  if (ss == 0.0) {
-    beta = alpha; tau = 0.0; scal = 0.0;
-  } else {
-    beta = -copysign(hypot(alpha, sqrt(ss)), alpha);
-    tau = (beta - alpha) / beta;
-    scal = 1.0 / (alpha - beta);
-  }
-  if (g == 0 && threadIdx.x == 0) {
-    a.dd[(size_t)z * n + j] = dj;
-    a.ee[(size_t)z * n + j] = beta;
-    a.tau[(size_t)z * n + j] = tau;
-  }
-  __syncthreads();                 // alpha and d have been read by everyone
-  for (int i = j + threadIdx.x; i < n; i += TDT) xs[i] = (i == j) ? 0.0 : ((i == j + 1) ? 1.0 : xs[i] * scal);
-  __syncthreads();
-  int r0, r1;
-  chunk_of(j, n, G, g, r0, r1);
-  double* VHj = a.VH + (size_t)z * n * ldn + (size_t)j * ldn;
-  for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
-    if (jj > 0) {
-      const double wfin = __ldcg(wbuf + i) - gamma * __ldcg(vprev + i);
-      Z1[(size_t)i * 2 * NBT + NBT + jj - 1] = wfin;
-      Z2[(size_t)i * 2 * NBT + jj - 1] = wfin;
-    }
-    if (i >= j + 1) {
-      const double v = xs[i];
-      VHj[i] = v;
-      Z1[(size_t)i * 2 * NBT + jj] = v;
-      Z2[(size_t)i * 2 * NBT + NBT + jj] = v;
-      vnew[i] = v;
-    }
-  }
-  __syncthreads();
-  // y = A v for the CTA's rows (columns from the even column c0 <= j+1; xs[j] = 0, pad columns are zero)
-  const int c0 = (j + 1) & ~1;
-  const int rs = max(r0, j + 1);
-  for (int i = rs + warp; i < r1; i += TDW) {
-    const double* row = Cm + (size_t)i * ldn;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = c0 + 2 * lane;
-    for (; k + 192 < ldn; k += 256) {
-      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
-      const double2 a1 = __ldg(reinterpret_cast<const double2*>(row + k + 64));
-      const double2 a2 = __ldg(reinterpret_cast<const double2*>(row + k + 128));
-      const double2 a3 = __ldg(reinterpret_cast<const double2*>(row + k + 192));
-      const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
-      const double2 x1 = *reinterpret_cast<const double2*>(xs + k + 64);
-      const double2 x2 = *reinterpret_cast<const double2*>(xs + k + 128);
-      const double2 x3 = *reinterpret_cast<const double2*>(xs + k + 192);
-      s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
-      s1 = fma(a1.x, x1.x, s1); s1 = fma(a1.y, x1.y, s1);
-      s2 = fma(a2.x, x2.x, s2); s2 = fma(a2.y, x2.y, s2);
-      s3 = fma(a3.x, x3.x, s3); s3 = fma(a3.y, x3.y, s3);
-    }
-    for (; k < ldn; k += 64) {
-      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
-      const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
-      s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
-    }
-    const double s = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) ybuf[i] = s;
-  }
-  // partial (panel col)^T v over the CTA's rows, columns c' < jj of V and W (W column jj-1 was finalised above)
-  {
-    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    double acc = 0.0;
-    if ((col & (NBT - 1)) < jj)
-      for (int i = rs + rg; i < r1; i += 8) acc = fma(__ldcg(Z1 + (size_t)i * 2 * NBT + col), xs[i], acc);
-    tred[rg * 2 * NBT + col] = acc;
-    __syncthreads();
-    if (threadIdx.x < 2 * NBT) {
-      double t = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += tred[q * 2 * NBT + threadIdx.x];
-      a.tpart[((size_t)z * G + g) * 2 * NBT + threadIdx.x] = t;
-    }
-    __syncthreads();
-  }
-}
-
-// end of panel: W[:, pw-1] = w - gamma v for rows >= r
-__device__ __forceinline__ void td_phase3(const TdPanel& a, double* ex, int z, int g, int G, int r, int pw) {
-  const int n = a.n;
-  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
-  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
-  const double* wbuf = a.wbuf + (size_t)z * n;
-  const double* vprev = a.vcur + ((size_t)z * 2 + ((pw + 1) & 1)) * n;
-  const double gamma = td_gamma(a, ex, z, G, r, pw);
-  int r0, r1;
-  chunk_of(r, n, G, g, r0, r1);
-  for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
-    const double wfin = __ldcg(wbuf + i) - gamma * __ldcg(vprev + i);
-    Z1[(size_t)i * 2 * NBT + NBT + pw - 1] = wfin;
-    Z2[(size_t)i * 2 * NBT + pw - 1] = wfin;
-  }
-}
-
-__global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdPanel a, int k0, int pw) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) double td_sm[];
-  double* xs = td_sm;                 // [ldn]
-  double* ex = td_sm + a.ldn;         // scratch
-  const int nz = a.nz, z = blockIdx.x % nz, g = blockIdx.x / nz, G = gridDim.x / nz;
-  for (int i = threadIdx.x; i < a.ldn; i += TDT) xs[i] = 0.0;
-  __syncthreads();
-  for (int jj = 0; jj < pw; ++jj) {
-    const int j = k0 + jj;
-    td_phase1(a, ex, z, g, G, j, jj, false);
-    grid.sync();
-    td_phase2(a, xs, ex, z, g, G, j, jj);
-    grid.sync();
-  }
-  const int r = k0 + pw;
-  if (r < a.n) {
-    td_phase1(a, ex, z, g, G, r, pw, true);
-    grid.sync();
-    td_phase3(a, ex, z, g, G, r, pw);
   }
 }
 
@@ -795,7 +517,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.colbuf, vec));
   APV_TRY(al((void**)&ws.ybuf, vec));
   APV_TRY(al((void**)&ws.wbuf, vec));
-  APV_TRY(al((void**)&ws.part, (size_t)nz * GMAX * (2 * NBT + 1) * sizeof(double)));
+  APV_TRY(al((void**)&ws.tdws, tridiag_scratch_doubles(n, nz) * sizeof(double)));
   APV_TRY(al((void**)&ws.vcur, (size_t)nz * 2 * n * sizeof(double)));
   APV_TRY(al((void**)&ws.lam, (size_t)nz * V * sizeof(double)));
   APV_TRY(al((void**)&ws.shift, (size_t)nz * V * sizeof(double) + (size_t)nz * 4 * sizeof(double)));
@@ -812,7 +534,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.part, ws.vcur, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
@@ -906,37 +628,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
 
   APV_CUDA_TRY(cudaEventRecord(ws.ev[2], st));
   // ---- blocked Householder tridiagonalisation of Cm
-  {
-    int dev = 0, sms = 0;
-    APV_CUDA_TRY(cudaGetDevice(&dev));
-    APV_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int G = std::max(1, std::min(std::min(sms / nz, GMAX), ceil_div(n, 16)));
-    const size_t tdsm = (size_t)(ldn + TD_EXTRA) * sizeof(double);
-    APV_TRY(ensure_smem(td_panel_kernel, tdsm));
-    TdPanel tp{ws.Cm, ws.VH, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf, ws.ybuf, ws.wbuf, ws.vcur,
-               ws.part, ws.part + (size_t)nz * GMAX, n, ldn, nz};
-    for (int k0 = 0; k0 < n; k0 += NBT) {
-      int pw = std::min(NBT, n - k0);
-      int k0v = k0;
-      void* args[] = {(void*)&tp, (void*)&k0v, (void*)&pw};
-      APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT)], st));
-      APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)td_panel_kernel, dim3(G * nz), dim3(TDT), args, tdsm, st));
-      APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT) + 1], st));
-      ++nl;
-      const int r = k0 + pw;
-      if (r < n) {         // A22 -= V W^T + W V^T
-        GemmArgs u{};
-        u.batch = nz;
-        u.A = ws.Z1 + (size_t)r * 2 * NBT; u.lda = 2 * NBT; u.strideA = (long long)n * 2 * NBT;
-        u.B = ws.Z2 + (size_t)r * 2 * NBT; u.ldb = 2 * NBT; u.strideB = (long long)n * 2 * NBT;
-        u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
-        u.M = n - r; u.N = n - r; u.K = 2 * NBT; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
-        APV_TRY(gemm_f64(u, st));
-        ++nl;
-      }
-    }
-  }
-
+  APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));
   // ---- top-V eigenpairs of T
   double* tnorm = ws.shift + (size_t)nz * V;

@@ -1,0 +1,87 @@
+"""GPU: (1) acoustic contrast / normalised signal distortion of the rendered feeds within 0.01 dB of the oracle
+(north_star criterion); (2) block-range sharding with the CUDA engine, two ranks emulated on one GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(nblk=14, seed=31):
+    rng = np.random.default_rng(seed)
+    K, L, M = 64, 4, 3
+    dec = np.exp(-np.arange(K) / 16.0).reshape(-1, 1, 1)
+    rA = 1e-3 * rng.standard_normal((K, L, M)) * dec
+    rB = 1e-3 * rng.standard_normal((K, L, M)) * dec
+    cfg = dict(block_size=128, filter_length=16, modeling_delay=4, reference_index_A=1, reference_index_B=2,
+               number_of_eigenvectors=12, mu=1.0, statistics_buffer_length=192, perceptual=False)
+    sA, sB = rng.standard_normal(nblk * 64), rng.standard_normal(nblk * 64)
+    return rA, rB, cfg, sA, sB, nblk
+
+
+def test_contrast_and_distortion_within_001_db():
+    from ap_vast_unofficial_b200 import apvast
+    from ap_vast_unofficial_b200.metrics import evaluate_zone
+    from oracle.apvast_oracle import ApvastOracle
+    rA, rB, cfg, sA, sB, nblk = _case()
+    feeds = {}
+    for name, cls in (("gpu", apvast), ("ora", ApvastOracle)):
+        np.random.seed(0)
+        eng = cls(rir_A=rA, rir_B=rB, **cfg)
+        oa, ob = [], []
+        for t in range(nblk):
+            A, B, _, _ = eng.process_input_buffers(sA[t * 64:(t + 1) * 64], sB[t * 64:(t + 1) * 64])
+            oa.append(np.stack(A)); ob.append(np.stack(B))
+        feeds[name] = (np.concatenate(oa, axis=1), np.concatenate(ob, axis=1))     # (V, T, L)
+    for v in (0, 5, 11):
+        for z, (rb, rd, sig, ref) in enumerate(((rA, rB, sA, 1), (rB, rA, sB, 2))):
+            ac_g, nsd_g = evaluate_zone(feeds["gpu"][z][v][5 * 64:], rb, rd, sig[5 * 64:], ref, 4)
+            ac_o, nsd_o = evaluate_zone(feeds["ora"][z][v][5 * 64:], rb, rd, sig[5 * 64:], ref, 4)
+            assert abs(ac_g - ac_o) < 0.01, (v, z, ac_g, ac_o)
+            assert abs(nsd_g - nsd_o) < 0.01, (v, z, nsd_g, nsd_o)
+
+
+class _FakeDist:
+    """Two ranks run one after the other on one GPU; point-to-point messages go through a dict."""
+    box = {}
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def get_backend(self):
+        return "gloo"
+
+    def get_world_size(self):
+        return 2
+
+    class _Req:
+        def wait(self):
+            return None
+
+    def isend(self, t, dst):
+        _FakeDist.box[(self.rank, dst)] = t.clone()
+        return self._Req()
+
+    def irecv(self, t, src):
+        t.copy_(_FakeDist.box[(src, self.rank)])
+        return self._Req()
+
+    def all_gather_object(self, out, obj):
+        for i in range(len(out)):
+            out[i] = obj if i == self.rank else []
+
+
+def test_sharded_two_ranks_emulated_matches_single_stream():
+    from ap_vast_unofficial_b200 import apvast
+    from ap_vast_unofficial_b200.sharded import process_signal_sharded
+    rA, rB, cfg, sA, sB, nblk = _case(nblk=16, seed=33)
+    make = lambda: apvast(rir_A=rA, rir_B=rB, **cfg)
+    ref = process_signal_sharded(make, sA, sB, seed=0)
+    r0 = process_signal_sharded(make, sA, sB, rank=0, world=2, dist=_FakeDist(0), seed=0)
+    r1 = process_signal_sharded(make, sA, sB, rank=1, world=2, dist=_FakeDist(1), seed=0)
+    assert r0["blocks"] == (0, 8) and r1["blocks"] == (8, 16)
+    outs = r0["out_A"] + r1["out_A"]
+    ws = r0["w_A"] + r1["w_A"]
+    for t in range(16):
+        assert np.linalg.norm(outs[t] - ref["out_A"][t]) <= 1e-8 * np.linalg.norm(ref["out_A"][t]), t
+        for v in range(ws[t].shape[0]):
+            assert np.linalg.norm(ws[t][v] - ref["w_A"][t][v]) <= 1e-8 * np.linalg.norm(ref["w_A"][t][v]), (t, v)
