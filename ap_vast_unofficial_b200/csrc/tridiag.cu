@@ -3,27 +3,26 @@
 // Python/apvast.py:30).  Lower variant of LAPACK dsytrd/dlatrd on a fully stored symmetric matrix,
 // panel width NBT = 32, both zone problems in the same launches.
 //
-// ONE persistent cooperative kernel per panel, two grid barriers per column:
+// Panel storage: Z1[i][0..NBT) = V, Z1[i][NBT..2NBT) = W;  Z2[i][0..NBT) = W, Z2[i][NBT..2NBT) = V, so that
+// the trailing update A22 -= V W^T + W V^T is one DMMA GEMM  A22 -= Z1 Z2^T  with K = 2 NBT (issued by
+// the host between panel kernels).
 //
-//   phase A(j)  every CTA gathers the updated column x (both zones) into shared memory and derives the
-//               reflector scalars (beta, tau, 1/(alpha-beta)) redundantly.  The symmetric product
-//               y' = A x is formed from the LOWER triangle only: the triangle is cut into TB x TB tiles
-//               dealt round-robin to the CTAs; a tile yields a row part (y'_I += A_IK x_K) and a column
-//               part (y'_K += A_IK^T x_I) that are written as per-tile partial vectors (deterministic,
-//               no atomics).  Halving the bytes keeps the trailing matrices of both zones L2-resident
-//               for most of the factorisation.  The CTA also accumulates its share of x^T A x and, over
-//               its row chunk, the panel products V^T v and W^T v.
-//   --- grid barrier ---
-//   phase B(j)  one reduction gives V^T v, W^T v and v^T A v, hence
-//                   w.v = tau (v^T A v - 2 (V^T v).(W^T v)),   gamma = tau/2 (w.v)
-//               without a second reduction; per row of the CTA's chunk: y (assembled from the tile
-//               partials), w = tau (y - V W^T v - W V^T v) - gamma v  (final W column), and the next
-//               column  x = A[j+1, :] - sum_c (V[:,c] W[j+1,c] + W[:,c] V[j+1,c]).
-//   --- grid barrier ---
+// ONE persistent cooperative kernel per panel of NBT columns, two grid barriers per column:
 //
-// v = s x + c e_{j+1} (s = 1/(alpha-beta), c = 1 - s alpha) is never materialised for the product:
-// A v = s (A x) + c A[:, j+1], so the big read starts before the norm reduction has finished.
-// Panel end: A22 -= V W^T + W V^T as one DMMA GEMM (K = 64) issued by the host between panel kernels.
+//   phase P1(j): (jj > 0) raw w of the previous column,  w = tau (y - V (W^T v) - W (V^T v)),  its
+//                partial w.v, and the updated column j as a function of the still unknown
+//                gamma = tau/2 (w.v):   x = a + 2 gamma v_prev   (a goes to colbuf)
+//   --- grid barrier ---
+//   phase P2(j): gamma, x and the reflector scalars (beta, tau, s = 1/(alpha-beta)) -- every CTA
+//                redundantly, it needs all of x for its GEMV rows anyway --, final W column of the
+//                previous reflector, y = A[j+1:, j+1:] v for the CTA's rows (the HBM/L2-bound part:
+//                4 x 16-byte loads in flight per lane, 16 warps per SM), partial (panel)^T v.
+//                v = s x + c e_{j+1} (c = 1 - s alpha) is not materialised for the product:
+//                A v = s (A x) + c A[:, j+1], so no rescaling pass sits in front of the big read.
+//   --- grid barrier ---
+// CTAs are split between the zone problems (zone = blockIdx.x % nz).  Everything another CTA wrote
+// during the kernel is read with ld.global.cg (L2), never through the non-coherent L1; independent
+// loads are issued ahead of the reductions they do not depend on (the phases are latency chains).
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -38,421 +37,353 @@ namespace apv {
 
 namespace {
 
-constexpr int NBT = 32;            // panel width (one V and one W column per lane)
-constexpr int TDT = 512;           // threads per CTA
-constexpr int TDW = TDT / 32;      // warps per CTA
-constexpr int TBMAX = 256;         // largest GEMV tile
-constexpr int NTMAX = 33;          // tiles per dimension (n <= 8448 with 256-wide tiles)
-constexpr int TILEMAX = NTMAX * (NTMAX + 1) / 2;
-constexpr int CTAMAX = 256;        // upper bound of CTAs in the panel kernel
-constexpr int NPART = 2 * NBT + 2; // per-CTA partials: V^T v [32], W^T v [32], x^T A x, spare
+constexpr int NBT = 32;         // panel width (one V and one W column per lane)
+constexpr int GMAX = 256;       // upper bound of CTAs per zone
+constexpr int TDT = 512;        // threads per CTA
+constexpr int TDW = TDT / 32;
+constexpr int TD_TS = 0, TD_TRED = 2 * NBT, TD_RED = TD_TRED + 8 * 2 * NBT, TD_SC = TD_RED + 40, TD_EXTRA = TD_SC + 8;
 
-struct TdArgs {
+struct TdPanel {
   double* Cm; double* VH; double* Z1; double* Z2; double* tau; double* dd; double* ee;
-  double* xbuf;    // [nz][n]                 updated column j (rows >= j)
-  double* pn;      // [nz][CTAMAX]            partial |x[j+2:]|^2
-  double* parts;   // [CTAMAX][nz][NPART]
-  double* prow;    // [nz][TILEMAX][TBMAX]    tile row parts of A x
-  double* pcol;    // [nz][TILEMAX][TBMAX]    tile column parts of A x
+  double* colbuf; double* ybuf; double* wbuf;
+  double* vcur;   // [nz][2][n]        current reflector, double buffered by column parity
+  double* pwv;    // [nz][GMAX]        partial w.v
+  double* tpart;  // [nz][GMAX][2 NBT] partial (panel col)^T v
   int n, ldn, nz;
-  long long* dbg;  // optional clock64 accumulators (APV_TD_DEBUG)
+  long long* dbg;
 };
 
-#define TD_TICK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { long long _t = clock64(); a.dbg[k] += _t - *tk; *tk = _t; } } while (0)
-
-// shared-memory scratch layout (doubles) behind xs[nz][ldn] and cb[TDW][TBMAX]
-constexpr int EX_TS = 0;                       // reduced V^T v | W^T v           [2 NBT]
-constexpr int EX_TRED = EX_TS + 2 * NBT;       // 8-way partials of the above     [8][2 NBT]
-constexpr int EX_RED = EX_TRED + 8 * 2 * NBT;  // block_sum scratch               [40]
-constexpr int EX_SC = EX_RED + 40;             // per-zone scalars                [2][8]
-constexpr int EX_MISC = EX_SC + 16;            // misc                            [16]
-constexpr int EX_SIZE = EX_MISC + 16;
-enum { SC_SS = 0, SC_DJ, SC_ALPHA, SC_BETA, SC_TAU, SC_S, SC_C };
+#define TD_TICK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { long long _t = clock64(); a.dbg[k] += _t - tk; tk = _t; } } while (0)
 
 __device__ __forceinline__ void chunk_of(int lo, int hi, int G, int g, int& a, int& b) {
-  const int rows = max(hi - lo, 0), per = (rows + G - 1) / G;
+  const int rows = hi - lo, per = (rows + G - 1) / G;
   a = lo + g * per;
   b = min(hi, a + per);
 }
 
-__device__ __forceinline__ int tile_size(int m) {    // ~16 tiles per dimension, 64 <= TB <= 256
-  int tb = 64;
-  while (tb < TBMAX && m > 16 * tb) tb <<= 1;
-  return tb;
-}
-
-struct Geo {
-  int base, tb, nt, ntile;
-};
-__device__ __forceinline__ Geo geometry(int n, int j) {
-  Geo g;
-  g.base = (j + 1) & ~1;                 // even, so that 16-byte loads are aligned; x[j] is forced to 0
-  g.tb = tile_size(n - j - 1);
-  g.nt = (n - g.base + g.tb - 1) / g.tb;
-  g.ntile = g.nt * (g.nt + 1) / 2;
-  return g;
-}
-
-// ---- start of a panel: x = A[k0, k0:n]
-__device__ void td_phaseX(const TdArgs& a, double* ex, int k0) {
-  const int n = a.n, nz = a.nz;
-  const int z = blockIdx.x % nz, g = blockIdx.x / nz, G = gridDim.x / nz;
-  if (g >= G) return;
+__device__ __forceinline__ void td_phase1(const TdPanel& a, double* ex, int z, int g, int G, int j, int jj,
+                                          bool w_only) {
+  const int n = a.n, ldn = a.ldn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* ts = ex + TD_TS;
+  double* tred = ex + TD_TRED;
+  double* red = ex + TD_RED;
+  const double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  const double* Cm = a.Cm + (size_t)z * n * ldn;
+  double* colbuf = a.colbuf + (size_t)z * n;
+  double* wbuf = a.wbuf + (size_t)z * n;
+  const double* ybuf = a.ybuf + (size_t)z * n;
+  const double* vprev = a.vcur + ((size_t)z * 2 + ((jj + 1) & 1)) * n;   // written in P2 of column j-1
   int r0, r1;
-  chunk_of(k0, n, G, g, r0, r1);
-  const double* row = a.Cm + (size_t)z * n * a.ldn + (size_t)k0 * a.ldn;
-  double ss = 0.0;
-  for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
-    const double x = row[i];
-    a.xbuf[(size_t)z * n + i] = x;
-    if (i >= k0 + 2) ss = fma(x, x, ss);
+  chunk_of(j, n, G, g, r0, r1);
+  if (jj == 0) {
+    for (int i = r0 + threadIdx.x; i < r1; i += TDT) colbuf[i] = Cm[(size_t)j * ldn + i];
+    return;
   }
-  ss = block_sum(ss, ex + EX_RED);
-  if (threadIdx.x == 0) a.pn[(size_t)z * CTAMAX + g] = ss;
-}
-
-// ---- phase A
-__device__ void td_phaseA(const TdArgs& a, double* xs, double* cb, double* ex, int j, int jj, long long* tk) {
-  const int n = a.n, ldn = a.ldn, nz = a.nz;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int zb = b % nz, gb = b / nz, G = nb / nz;
-  double* sc = ex + EX_SC;
-  // 1. gather x of every zone; x[j] goes to the scalar slot and is zeroed in the vector
-  for (int z = 0; z < nz; ++z)
-    for (int i = j + threadIdx.x; i < n; i += TDT) {
-      const double x = __ldcg(a.xbuf + (size_t)z * n + i);
-      if (i == j) { sc[z * 8 + SC_DJ] = x; xs[z * ldn + i] = 0.0; }
-      else xs[z * ldn + i] = x;
-    }
-  if (warp < nz) {
+  const int nc = jj - 1;                       // finished panel columns
+  // loads that do not depend on the reduction: row-j panel entries, y_j, tau
+  double Vj = 0.0, Wj = 0.0;
+  if (lane < nc) {
+    Vj = __ldcg(Z1 + (size_t)j * 2 * NBT + lane);
+    Wj = __ldcg(Z1 + (size_t)j * 2 * NBT + NBT + lane);
+  }
+  const double yj = __ldcg(ybuf + j);
+  const double tau_p = __ldcg(a.tau + (size_t)z * n + j - 1);
+  {  // reduce the partial panel^T v of column j-1 (columns c' < jj-1 of V and of W)
+    const int col = threadIdx.x & 63, qg = threadIdx.x >> 6;       // 8 groups of 64
     double s = 0.0;
-    for (int q = lane; q < G; q += 32) s += __ldcg(a.pn + (size_t)warp * CTAMAX + q);
-    s = warp_sum(s);
-    if (lane == 0) sc[warp * 8 + SC_SS] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < nz) {
-    const int z = threadIdx.x;
-    const double ss = sc[z * 8 + SC_SS];
-    const double alpha = (j + 1 < n) ? xs[z * ldn + j + 1] : 0.0;
-    double beta, tau, s;
-    if (ss == 0.0) { beta = alpha; tau = 0.0; s = 0.0; }
-    else {
-      beta = -copysign(hypot(alpha, sqrt(ss)), alpha);
-      tau = (beta - alpha) / beta;
-      s = 1.0 / (alpha - beta);
+    if ((col & (NBT - 1)) < nc) {
+      const double* tp = a.tpart + (size_t)z * GMAX * 2 * NBT;
+      for (int q = qg; q < G; q += 8) s += __ldcg(tp + (size_t)q * 2 * NBT + col);
     }
-    sc[z * 8 + SC_ALPHA] = alpha; sc[z * 8 + SC_BETA] = beta; sc[z * 8 + SC_TAU] = tau;
-    sc[z * 8 + SC_S] = s; sc[z * 8 + SC_C] = 1.0 - s * alpha;
-    if (b == 0) {
-      a.dd[(size_t)z * n + j] = sc[z * 8 + SC_DJ];
-      if (j + 1 < n) { a.ee[(size_t)z * n + j] = beta; a.tau[(size_t)z * n + j] = tau; }
-    }
-  }
-  if (j >= n - 1) { __syncthreads(); return; }
-
-  TD_TICK(0);
-  // 2. tiles of the lower triangle: row parts, column parts, x^T A x
-  const Geo ge = geometry(n, j);
-  const int tb = ge.tb, rpw = tb / TDW, q2 = tb / 64;     // rows per warp; double2 per lane and row
-  double xax0 = 0.0, xax1 = 0.0;
-  for (int tile = b; tile < ge.ntile * nz; tile += nb) {
-    const int z = tile / ge.ntile;
-    int t = tile - z * ge.ntile, I = 0;
-    while (t >= I + 1) { t -= I + 1; ++I; }
-    const int K = t;
-    const bool offd = I > K;
-    const int r0 = ge.base + I * tb, k0 = ge.base + K * tb;
-    const double* A = a.Cm + (size_t)z * n * ldn;
-    const double* x = xs + z * ldn;
-    const int tix = (tile - z * ge.ntile);
-    double* prow = a.prow + ((size_t)z * TILEMAX + tix) * TBMAX;
-    double colacc[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) colacc[u] = 0.0;
-    double myx = 0.0;
-    for (int rr = 0; rr < rpw; rr += 4) {
-      double2 av[4][4];
-      double xi[4];
-      int ii[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        ii[r] = r0 + warp * rpw + rr + r;
-        const bool rowok = (rr + r < rpw) && ii[r] < n;
-        xi[r] = rowok ? x[ii[r]] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + 2 * lane + 64 * u;
-          av[r][u] = (rowok && u < q2 && k < ldn && (offd || k <= ii[r]))
-                         ? __ldg(reinterpret_cast<const double2*>(A + (size_t)ii[r] * ldn + k))
-                         : make_double2(0.0, 0.0);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        double racc = 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + 2 * lane + 64 * u;
-          if (u < q2 && k < ldn) {
-            const double2 xv = *reinterpret_cast<const double2*>(x + k);
-            const bool m0 = offd || k <= ii[r], m1 = offd || k + 1 <= ii[r];
-            const bool c0 = offd || k < ii[r], c1 = offd || k + 1 < ii[r];
-            racc = fma(m0 ? av[r][u].x : 0.0, xv.x, racc);
-            racc = fma(m1 ? av[r][u].y : 0.0, xv.y, racc);
-            colacc[2 * u] = fma(c0 ? av[r][u].x : 0.0, xi[r], colacc[2 * u]);
-            colacc[2 * u + 1] = fma(c1 ? av[r][u].y : 0.0, xi[r], colacc[2 * u + 1]);
-          }
-        }
-        racc = warp_sum(racc);
-        if (lane == 0 && (rr + r < rpw) && ii[r] < n) {
-          prow[ii[r] - r0] = racc;
-          myx = fma(racc, xi[r], myx);
-        }
-      }
-    }
-    // cross-warp reduction of the column parts
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (u < q2) {
-        cb[warp * TBMAX + 2 * lane + 64 * u] = colacc[2 * u];
-        cb[warp * TBMAX + 2 * lane + 64 * u + 1] = colacc[2 * u + 1];
-      }
-    __syncthreads();
-    if (threadIdx.x < tb) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < TDW; ++w) s += cb[w * TBMAX + threadIdx.x];
-      a.pcol[((size_t)z * TILEMAX + tix) * TBMAX + threadIdx.x] = s;
-      const int k = k0 + threadIdx.x;
-      if (k < n) myx = fma(s, x[k], myx);
-    }
-    __syncthreads();
-    if (z == 0) xax0 += myx; else xax1 += myx;
-  }
-
-  __syncthreads();       // scalars of step 1 visible even to CTAs that own no tile
-  TD_TICK(1);
-  // 3. panel products over the CTA's row chunk, v stored
-  if (gb < G) {
-    const double s = sc[zb * 8 + SC_S];
-    const double* x = xs + zb * ldn;
-    int r0, r1;
-    chunk_of(j + 1, n, G, gb, r0, r1);
-    double* Z1 = a.Z1 + (size_t)zb * n * 2 * NBT;
-    double* Z2 = a.Z2 + (size_t)zb * n * 2 * NBT;
-    double* VHj = a.VH + (size_t)zb * n * ldn + (size_t)j * ldn;
-    for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
-      const double v = (i == j + 1) ? 1.0 : s * x[i];
-      VHj[i] = v;
-      Z1[(size_t)i * 2 * NBT + jj] = v;
-      Z2[(size_t)i * 2 * NBT + NBT + jj] = v;
-    }
-    double* tred = ex + EX_TRED;
-    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    double acc = 0.0;
-    if ((col & (NBT - 1)) < jj)
-      for (int i = r0 + rg; i < r1; i += 8) {
-        const double v = (i == j + 1) ? 1.0 : s * x[i];
-        acc = fma(__ldcg(Z1 + (size_t)i * 2 * NBT + col), v, acc);
-      }
-    tred[rg * 2 * NBT + col] = acc;
-  }
-  // 4. block totals
-  double* red = ex + EX_RED;
-  const double x0 = block_sum(xax0, red);
-  const double x1 = nz > 1 ? block_sum(xax1, red) : 0.0;
-  double* P = a.parts + (size_t)b * nz * NPART;
-  if (threadIdx.x < 2 * NBT) {
-    double t = 0.0;
-    if (gb < G) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += (ex + EX_TRED)[q * 2 * NBT + threadIdx.x];
-    }
-    P[(size_t)zb * NPART + threadIdx.x] = t;
-  }
-  if (threadIdx.x == 0) {
-    P[2 * NBT] = x0;
-    if (nz > 1) P[NPART + 2 * NBT] = x1;
-  }
-}
-
-// ---- phase B
-__device__ void td_phaseB(const TdArgs& a, double* xs, double* ex, int j, int jj, bool last, long long* tk) {
-  const int n = a.n, ldn = a.ldn, nz = a.nz;
-  if (j >= n - 1) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x, nb = gridDim.x;
-  const int zb = b % nz, gb = b / nz, G = nb / nz;
-  if (gb >= G) return;
-  double* sc = ex + EX_SC + zb * 8;
-  double* ts = ex + EX_TS;
-  double* tred = ex + EX_TRED;
-  double* misc = ex + EX_MISC;
-  const double* x = xs + zb * ldn;
-  const double* A = a.Cm + (size_t)zb * n * ldn;
-  double* Z1 = a.Z1 + (size_t)zb * n * 2 * NBT;
-  double* Z2 = a.Z2 + (size_t)zb * n * 2 * NBT;
-  const Geo ge = geometry(n, j);
-  const double* prow = a.prow + (size_t)zb * TILEMAX * TBMAX;
-  const double* pcol = a.pcol + (size_t)zb * TILEMAX * TBMAX;
-
-  // assemble (A x)_i from the tile partial vectors (all lanes of a warp cooperate)
-  auto ax_of = [&](int i) -> double {
-    const int I = (i - ge.base) / ge.tb, il = (i - ge.base) - I * ge.tb;
-    double s = 0.0;
-    for (int K = lane; K <= I; K += 32) s += __ldcg(prow + (size_t)(I * (I + 1) / 2 + K) * TBMAX + il);
-    for (int I2 = I + lane; I2 < ge.nt; I2 += 32) s += __ldcg(pcol + (size_t)(I2 * (I2 + 1) / 2 + I) * TBMAX + il);
-    return warp_sum(s);
-  };
-
-  // 1. reductions: V^T v, W^T v over the G CTAs of this zone; x^T A x over all CTAs
-  {
-    const int col = threadIdx.x & 63, qg = threadIdx.x >> 6;
-    double s = 0.0;
-    if ((col & (NBT - 1)) < jj)
-      for (int q = qg; q < G; q += 8) s += __ldcg(a.parts + ((size_t)(q * nz + zb) * nz + zb) * NPART + col);
     tred[qg * 2 * NBT + col] = s;
-    double xa = 0.0;
-    for (int q = threadIdx.x; q < nb; q += TDT) xa += __ldcg(a.parts + ((size_t)q * nz + zb) * NPART + 2 * NBT);
-    xa = block_sum(xa, ex + EX_RED);          // (barriers inside also publish tred)
+    __syncthreads();
     if (threadIdx.x < 2 * NBT) {
       double t = 0.0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) t += tred[q * 2 * NBT + threadIdx.x];
       ts[threadIdx.x] = t;
     }
-    if (threadIdx.x == 0) misc[0] = xa;
     __syncthreads();
   }
-  TD_TICK(4);
-  const double tau = sc[SC_TAU], s = sc[SC_S], c = sc[SC_C];
-  const int j1 = j + 1;
-  // 2. scalars every thread needs: gamma, and row j+1 of the final panel
-  double tW = 0.0, tV = 0.0, Vj1 = 0.0, Wj1 = 0.0;
-  if (lane < jj) {
-    tV = ts[lane];
-    tW = ts[NBT + lane];
-    Vj1 = __ldcg(Z1 + (size_t)j1 * 2 * NBT + lane);
-    Wj1 = __ldcg(Z1 + (size_t)j1 * 2 * NBT + NBT + lane);
-  }
-  const double ajj = A[(size_t)j1 * ldn + j1];
-  const double axj1 = ax_of(j1);
-  const double vAv = s * s * misc[0] + 2.0 * s * c * axj1 + c * c * ajj;
-  const double tvtw = warp_sum(tV * tW);
-  const double gamma = 0.5 * tau * (tau * (vAv - 2.0 * tvtw));
-  const double yj1 = s * axj1 + c * ajj;
-  const double wj1 = tau * (yj1 - warp_sum(Vj1 * tW + Wj1 * tV)) - gamma;     // final W[j+1][jj] (v_{j+1} = 1)
-
-  TD_TICK(5);
-  // 3. rows of the chunk
-  int r0, r1;
-  chunk_of(j1, n, G, gb, r0, r1);
-  const double* rowj1 = A + (size_t)j1 * ldn;
-  double ssn = 0.0;
-  for (int i = r0 + warp; i < r1; i += TDW) {
-    double Vi = 0.0, Wi = 0.0;
-    if (lane < jj) {
-      Vi = __ldcg(Z1 + (size_t)i * 2 * NBT + lane);
-      Wi = __ldcg(Z1 + (size_t)i * 2 * NBT + NBT + lane);
+  double tW = 0.0, tV = 0.0;
+  if (lane < nc) { tW = ts[NBT + lane]; tV = ts[lane]; }
+  // every CTA recomputes the raw w of row j (V[j][jj-1] = 1)
+  const double wj = tau_p * (yj - warp_sum(Vj * tW + Wj * tV));
+  double wv = 0.0;
+  for (int i0 = r0 + 2 * warp; i0 < r1; i0 += 2 * TDW) {
+    // two rows per trip; all loads are issued before the shuffles (same-address loads broadcast)
+    const int i1 = i0 + 1;
+    const bool ok1 = i1 < r1;
+    double V0 = 0.0, W0 = 0.0, V1 = 0.0, W1 = 0.0;
+    if (lane < nc) {
+      V0 = __ldcg(Z1 + (size_t)i0 * 2 * NBT + lane);
+      W0 = __ldcg(Z1 + (size_t)i0 * 2 * NBT + NBT + lane);
+      if (ok1) {
+        V1 = __ldcg(Z1 + (size_t)i1 * 2 * NBT + lane);
+        W1 = __ldcg(Z1 + (size_t)i1 * 2 * NBT + NBT + lane);
+      }
     }
-    const double aji = rowj1[i];                       // A[j+1][i] = A[i][j+1]
-    const double axi = ax_of(i);
-    const double cw = warp_sum(Vi * tW + Wi * tV);
-    const double cx = warp_sum(Vi * Wj1 + Wi * Vj1);
+    const double y0 = __ldcg(ybuf + i0), vp0 = __ldcg(vprev + i0);
+    const double y1 = ok1 ? __ldcg(ybuf + i1) : 0.0, vp1 = ok1 ? __ldcg(vprev + i1) : 0.0;
+    double c0 = 0.0, c1 = 0.0;
+    if (!w_only) {
+      c0 = Cm[(size_t)j * ldn + i0];
+      c1 = ok1 ? Cm[(size_t)j * ldn + i1] : 0.0;
+    }
+    const double cw0 = warp_sum(V0 * tW + W0 * tV), cx0 = warp_sum(V0 * Wj + W0 * Vj);
+    const double cw1 = warp_sum(V1 * tW + W1 * tV), cx1 = warp_sum(V1 * Wj + W1 * Vj);
     if (lane == 0) {
-      const double vi = (i == j1) ? 1.0 : s * x[i];
-      const double yi = s * axi + c * aji;
-      const double wf = tau * (yi - cw) - gamma * vi;  // final W[i][jj]
-      Z1[(size_t)i * 2 * NBT + NBT + jj] = wf;
-      Z2[(size_t)i * 2 * NBT + jj] = wf;
-      if (!last) {
-        const double xn = aji - cx - vi * wj1 - wf;    // column j+1 after the rank-2 updates (V[j+1][jj] = 1)
-        a.xbuf[(size_t)zb * n + i] = xn;
-        if (i >= j1 + 2) ssn = fma(xn, xn, ssn);
+      const double w0 = tau_p * (y0 - cw0);
+      wbuf[i0] = w0;
+      wv += w0 * vp0;
+      if (!w_only) colbuf[i0] = c0 - cx0 - vp0 * wj - w0;
+      if (ok1) {
+        const double w1 = tau_p * (y1 - cw1);
+        wbuf[i1] = w1;
+        wv += w1 * vp1;
+        if (!w_only) colbuf[i1] = c1 - cx1 - vp1 * wj - w1;
       }
     }
   }
-  if (!last) {
-    ssn = block_sum(ssn, ex + EX_RED);
-    if (threadIdx.x == 0) a.pn[(size_t)zb * CTAMAX + gb] = ssn;
+  if (lane == 0) red[warp] = wv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < TDW; ++w) s += red[w];
+    a.pwv[(size_t)z * GMAX + g] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double td_gamma(const TdPanel& a, double* ex, int z, int G, int j, int jj) {
+  if (jj == 0) return 0.0;
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int q = threadIdx.x; q < G; q += 32) s += __ldcg(a.pwv + (size_t)z * GMAX + q);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) ex[TD_SC] = 0.5 * __ldcg(a.tau + (size_t)z * a.n + j - 1) * s;
+  }
+  __syncthreads();
+  return ex[TD_SC];
+}
+
+__device__ __forceinline__ void td_phase2(const TdPanel& a, double* xs, double* ex, int z, int g, int G, int j,
+                                          int jj, long long& tk) {
+  const int n = a.n, ldn = a.ldn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tred = ex + TD_TRED;
+  double* red = ex + TD_RED;
+  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
+  const double* Cm = a.Cm + (size_t)z * n * ldn;
+  const double* colbuf = a.colbuf + (size_t)z * n;
+  const double* wbuf = a.wbuf + (size_t)z * n;
+  double* ybuf = a.ybuf + (size_t)z * n;
+  const double* vprev = a.vcur + ((size_t)z * 2 + ((jj + 1) & 1)) * n;
+  double* vnew = a.vcur + ((size_t)z * 2 + (jj & 1)) * n;
+  // the column and the previous reflector are fetched before gamma is known (independent loads)
+  constexpr int XPT = 16;                      // elements per thread: n <= XPT * TDT = 8192
+  double xa[XPT], xv[XPT];
+#pragma unroll
+  for (int u = 0; u < XPT; ++u) {
+    const int i = j + threadIdx.x + u * TDT;
+    xa[u] = (i < n) ? __ldcg(colbuf + i) : 0.0;
+    xv[u] = (i < n && jj > 0) ? __ldcg(vprev + i) : 0.0;
+  }
+  int r0, r1;
+  chunk_of(j, n, G, g, r0, r1);
+  const double gamma = td_gamma(a, ex, z, G, j, jj);
+  double ss = 0.0;
+#pragma unroll
+  for (int u = 0; u < XPT; ++u) {
+    const int i = j + threadIdx.x + u * TDT;
+    if (i < n) {
+      const double x = fma(2.0 * gamma, xv[u], xa[u]);
+      xs[i] = (i == j) ? 0.0 : x;            // xs[j] = 0: the GEMV may start at the even column <= j+1
+      if (i == j) ex[TD_SC + 1] = x;         // d_j
+      if (i >= j + 2) ss = fma(x, x, ss);
+    }
+  }
+  ss = block_sum(ss, red);                    // (its barriers also publish xs)
+  const double dj = ex[TD_SC + 1];
+  if (j == n - 1) {
+    if (g == 0 && threadIdx.x == 0) a.dd[(size_t)z * n + j] = dj;
+    return;
+  }
+  const double alpha = xs[j + 1];
+  double beta, tau, s;
+  if (ss == 0.0) {
+    beta = alpha; tau = 0.0; s = 0.0;
+  } else {
+    beta = -copysign(hypot(alpha, sqrt(ss)), alpha);
+    tau = (beta - alpha) / beta;
+    s = 1.0 / (alpha - beta);
+  }
+  const double c = 1.0 - s * alpha;            // v = s x + c e_{j+1}
+  if (g == 0 && threadIdx.x == 0) {
+    a.dd[(size_t)z * n + j] = dj;
+    a.ee[(size_t)z * n + j] = beta;
+    a.tau[(size_t)z * n + j] = tau;
+  }
+  double* VHj = a.VH + (size_t)z * n * ldn + (size_t)j * ldn;
+  for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
+    if (jj > 0) {
+      const double wfin = __ldcg(wbuf + i) - gamma * __ldcg(vprev + i);
+      Z1[(size_t)i * 2 * NBT + NBT + jj - 1] = wfin;
+      Z2[(size_t)i * 2 * NBT + jj - 1] = wfin;
+    }
+    if (i >= j + 1) {
+      const double v = (i == j + 1) ? 1.0 : s * xs[i];
+      VHj[i] = v;
+      Z1[(size_t)i * 2 * NBT + jj] = v;
+      Z2[(size_t)i * 2 * NBT + NBT + jj] = v;
+      vnew[i] = v;
+    }
+  }
+  TD_TICK(4);
+  // y = s (A x) + c A[:, j+1] for the CTA's rows; columns from the even column c0 <= j+1 (xs[j] = 0, pads are 0)
+  const int c0 = (j + 1) & ~1;
+  const int rs = max(r0, j + 1);
+  const double* rowj1 = Cm + (size_t)(j + 1) * ldn;      // A[i][j+1] = A[j+1][i]
+  for (int i = rs + warp; i < r1; i += TDW) {
+    const double* row = Cm + (size_t)i * ldn;
+    const double aj1 = rowj1[i];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = c0 + 2 * lane;
+    for (; k + 192 < ldn; k += 256) {
+      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
+      const double2 a1 = __ldg(reinterpret_cast<const double2*>(row + k + 64));
+      const double2 a2 = __ldg(reinterpret_cast<const double2*>(row + k + 128));
+      const double2 a3 = __ldg(reinterpret_cast<const double2*>(row + k + 192));
+      const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
+      const double2 x1 = *reinterpret_cast<const double2*>(xs + k + 64);
+      const double2 x2 = *reinterpret_cast<const double2*>(xs + k + 128);
+      const double2 x3 = *reinterpret_cast<const double2*>(xs + k + 192);
+      s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
+      s1 = fma(a1.x, x1.x, s1); s1 = fma(a1.y, x1.y, s1);
+      s2 = fma(a2.x, x2.x, s2); s2 = fma(a2.y, x2.y, s2);
+      s3 = fma(a3.x, x3.x, s3); s3 = fma(a3.y, x3.y, s3);
+    }
+    for (; k < ldn; k += 64) {
+      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
+      const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
+      s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
+    }
+    const double ax = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) ybuf[i] = fma(s, ax, c * aj1);
+  }
+  TD_TICK(5);
+  __syncthreads();        // the CTA's Z1 writes above are visible to its own threads
+  // partial (panel col)^T v over the CTA's rows, columns c' < jj of V and W (W column jj-1 was finalised above)
+  {
+    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    double acc = 0.0;
+    if ((col & (NBT - 1)) < jj)
+      for (int i = rs + rg; i < r1; i += 8) {
+        const double v = (i == j + 1) ? 1.0 : s * xs[i];
+        acc = fma(__ldcg(Z1 + (size_t)i * 2 * NBT + col), v, acc);
+      }
+    tred[rg * 2 * NBT + col] = acc;
+    __syncthreads();
+    if (threadIdx.x < 2 * NBT) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += tred[q * 2 * NBT + threadIdx.x];
+      a.tpart[((size_t)z * GMAX + g) * 2 * NBT + threadIdx.x] = t;
+    }
+    __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdArgs a, int k0, int pw) {
+// end of panel: W[:, pw-1] = w - gamma v for rows >= r
+__device__ __forceinline__ void td_phase3(const TdPanel& a, double* ex, int z, int g, int G, int r, int pw) {
+  const int n = a.n;
+  double* Z1 = a.Z1 + (size_t)z * n * 2 * NBT;
+  double* Z2 = a.Z2 + (size_t)z * n * 2 * NBT;
+  const double* wbuf = a.wbuf + (size_t)z * n;
+  const double* vprev = a.vcur + ((size_t)z * 2 + ((pw + 1) & 1)) * n;
+  const double gamma = td_gamma(a, ex, z, G, r, pw);
+  int r0, r1;
+  chunk_of(r, n, G, g, r0, r1);
+  for (int i = r0 + threadIdx.x; i < r1; i += TDT) {
+    const double wfin = __ldcg(wbuf + i) - gamma * __ldcg(vprev + i);
+    Z1[(size_t)i * 2 * NBT + NBT + pw - 1] = wfin;
+    Z2[(size_t)i * 2 * NBT + pw - 1] = wfin;
+  }
+}
+
+__global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdPanel a, int k0, int pw) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double td_sm[];
-  double* xs = td_sm;                                  // [nz][ldn]
-  double* cb = td_sm + (size_t)a.nz * a.ldn;           // [TDW][TBMAX]
-  double* ex = cb + TDW * TBMAX;
-  for (int i = threadIdx.x; i < a.nz * a.ldn; i += TDT) xs[i] = 0.0;
+  double* xs = td_sm;                 // [ldn]
+  double* ex = td_sm + a.ldn;         // scratch
+  const int nz = a.nz, z = blockIdx.x % nz, g = blockIdx.x / nz, G = gridDim.x / nz;
+  for (int i = threadIdx.x; i < a.ldn; i += TDT) xs[i] = 0.0;
   __syncthreads();
-  long long tkv = clock64();
-  long long* tk = &tkv;
-  td_phaseX(a, ex, k0);
-  grid.sync();
-  TD_TICK(8);
+  long long tk = clock64();
   for (int jj = 0; jj < pw; ++jj) {
     const int j = k0 + jj;
-    td_phaseA(a, xs, cb, ex, j, jj, tk);
+    td_phase1(a, ex, z, g, G, j, jj, false);
+    TD_TICK(0);
+    grid.sync();
+    TD_TICK(1);
+    td_phase2(a, xs, ex, z, g, G, j, jj, tk);
     TD_TICK(2);
     grid.sync();
     TD_TICK(3);
-    const bool last = jj == pw - 1;
-    td_phaseB(a, xs, ex, j, jj, last, tk);
-    TD_TICK(6);
-    if (!last) grid.sync();
-    TD_TICK(7);
+  }
+  const int r = k0 + pw;
+  if (r < a.n) {
+    td_phase1(a, ex, z, g, G, r, pw, true);
+    grid.sync();
+    td_phase3(a, ex, z, g, G, r, pw);
   }
 }
 
 }  // namespace
 
 size_t tridiag_scratch_doubles(int n, int nz) {
-  (void)n;
-  return (size_t)nz * CTAMAX + (size_t)CTAMAX * nz * NPART + 2 * (size_t)nz * TILEMAX * TBMAX;
+  return (size_t)nz * GMAX * (2 * NBT + 1) + (size_t)nz * 2 * n;
 }
 
 int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   const int n = ws.n, ldn = ws.ldn, nz = ws.nz;
-  if (ceil_div(n, TBMAX) > NTMAX - 1) {
-    snprintf(g_err, sizeof(g_err), "tridiagonalisation: n = %d exceeds the built tile table (n <= %d)", n, (NTMAX - 1) * TBMAX);
+  if (n > 16 * TDT) {
+    snprintf(g_err, sizeof(g_err), "tridiagonalisation: n = %d exceeds the built limit %d", n, 16 * TDT);
     return EINVAL_;
   }
   int dev = 0, sms = 0;
   APV_CUDA_TRY(cudaGetDevice(&dev));
   APV_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int ctas = std::min(std::min(sms, CTAMAX), std::max(1, ceil_div(n, 8)) * nz);
-  ctas = std::max(nz, ctas / nz * nz);
-  const size_t smem = ((size_t)nz * ldn + TDW * TBMAX + EX_SIZE) * sizeof(double);
+  const int G = std::max(1, std::min(std::min(sms / nz, GMAX), ceil_div(n, 16)));
+  const size_t smem = (size_t)(ldn + TD_EXTRA) * sizeof(double);
   static thread_local size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024 && smem > configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(td_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  TdArgs ta;
-  ta.Cm = ws.Cm; ta.VH = ws.VH; ta.Z1 = ws.Z1; ta.Z2 = ws.Z2; ta.tau = ws.tau; ta.dd = ws.dd; ta.ee = ws.ee;
-  ta.xbuf = ws.colbuf;
-  ta.pn = ws.tdws;
-  ta.parts = ta.pn + (size_t)nz * CTAMAX;
-  ta.prow = ta.parts + (size_t)CTAMAX * nz * NPART;
-  ta.pcol = ta.prow + (size_t)nz * TILEMAX * TBMAX;
-  ta.n = n; ta.ldn = ldn; ta.nz = nz;
+  TdPanel tp;
+  tp.Cm = ws.Cm; tp.VH = ws.VH; tp.Z1 = ws.Z1; tp.Z2 = ws.Z2; tp.tau = ws.tau; tp.dd = ws.dd; tp.ee = ws.ee;
+  tp.colbuf = ws.colbuf; tp.ybuf = ws.ybuf; tp.wbuf = ws.wbuf;
+  tp.pwv = ws.tdws;
+  tp.tpart = tp.pwv + (size_t)nz * GMAX;
+  tp.vcur = tp.tpart + (size_t)nz * GMAX * 2 * NBT;
+  tp.n = n; tp.ldn = ldn; tp.nz = nz;
   static long long* dbg = nullptr;
-  if (getenv("APV_TD_DEBUG") && !dbg) { cudaMalloc((void**)&dbg, 16 * sizeof(long long)); }
+  if (getenv("APV_TD_DEBUG") && !dbg) cudaMalloc((void**)&dbg, 16 * sizeof(long long));
   if (dbg) cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
-  ta.dbg = dbg;
+  tp.dbg = dbg;
   const long long mstride = (long long)n * ldn;
   for (int k0 = 0; k0 < n; k0 += NBT) {
     int pw = std::min(NBT, n - k0), k0v = k0;
-    void* args[] = {(void*)&ta, (void*)&k0v, (void*)&pw};
+    void* args[] = {(void*)&tp, (void*)&k0v, (void*)&pw};
     APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT)], st));
-    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)td_panel_kernel, dim3(ctas), dim3(TDT), args, smem, st));
+    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)td_panel_kernel, dim3(G * nz), dim3(TDT), args, smem, st));
     APV_CUDA_TRY(cudaEventRecord(ws.pev[2 * (k0 / NBT) + 1], st));
     ++*launches;
     const int r = k0 + pw;
-    if (r < n) {         // A22 -= V W^T + W V^T  (Z1 = [V | W], Z2 = [W | V])
+    if (r < n) {         // A22 -= V W^T + W V^T
       GemmArgs u{};
       u.batch = nz;
       u.A = ws.Z1 + (size_t)r * 2 * NBT; u.lda = 2 * NBT; u.strideA = (long long)n * 2 * NBT;
@@ -468,8 +399,8 @@ int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     cudaStreamSynchronize(st);
     cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost);
     const double us = 1.0 / 1965.0;
-    fprintf(stderr, "td dbg us: A.gather %.0f A.tiles %.0f A.rest %.0f sync1 %.0f | B.reduce %.0f B.scalars %.0f B.rows %.0f sync2 %.0f | X %.0f\n",
-            hd[0] * us, hd[1] * us, hd[2] * us, hd[3] * us, hd[4] * us, hd[5] * us, hd[6] * us, hd[7] * us, hd[8] * us);
+    fprintf(stderr, "td dbg us: P1 %.0f sync1 %.0f P2 %.0f (pre %.0f gemv %.0f) sync2 %.0f\n", hd[0] * us, hd[1] * us,
+            hd[2] * us, hd[4] * us, hd[5] * us, hd[3] * us);
   }
   return OK;
 }
