@@ -22,7 +22,8 @@ namespace apv {
 
 namespace {
 
-constexpr int NB = 64;    // Cholesky / TRSM block size
+constexpr int NB = 64;    // Cholesky / TRSM block size (diagonal blocks factorised / inverted in one CTA)
+constexpr int SB = 4 * NB; // super-block: width of the delayed rank-SB trailing updates
 constexpr int NBT = 32;   // tridiagonalisation panel width (one V and one W column per lane)
 
 struct Ptr2 {
@@ -377,6 +378,162 @@ __global__ void __launch_bounds__(32) eig_invit_kernel(const double* __restrict_
   for (int i = 0; i < n; ++i) X[i * S] *= inv;
 }
 
+// Same algorithm with the per-vector work arrays in shared memory: one CTA per eigenvector, thread 0 runs the
+// sequential recurrences at shared-memory latency, the other threads do the fills, norms and scalings.
+// Used when 5 n doubles + n flags fit in one SM's shared memory (n <= ~5000).   grid (V, nz), 128 threads.
+__device__ __forceinline__ double hash_uniform(unsigned long long key) {
+  unsigned long long x = key + 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+__device__ __forceinline__ double block_max128(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+}
+
+__global__ void __launch_bounds__(128) eig_invit_smem_kernel(const double* __restrict__ dd, const double* __restrict__ ee,
+                                                             const double* __restrict__ shift,
+                                                             const double* __restrict__ tnorm, double* __restrict__ iv,
+                                                             int* __restrict__ info, int n, int V, int Vp) {
+  extern __shared__ __align__(16) double ism[];
+  double* A = ism;
+  double* B = A + n;
+  double* C = B + n;
+  double* D2 = C + n;
+  double* X = D2 + n;
+  unsigned char* IN = reinterpret_cast<unsigned char*>(X + n);
+  __shared__ double red[8];
+  __shared__ double sh[4];
+  const int v = blockIdx.x, z = blockIdx.y;
+  const double* d = dd + (size_t)z * n;
+  const double* e = ee + (size_t)z * n;
+  double* Xout = iv + (size_t)z * 6 * n * Vp + 4 * (size_t)n * Vp + v;
+  const double lamv = shift[(size_t)z * V + v];
+  const double onenrm = tnorm[z * 4 + 0];
+  const double eps = DBL_EPSILON;
+  if (n == 1) {
+    if (threadIdx.x == 0) Xout[0] = 1.0;
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    A[i] = d[i] - lamv;
+    B[i] = (i < n - 1) ? e[i] : 0.0;
+    C[i] = (i < n - 1) ? e[i] : 0.0;
+    D2[i] = 0.0;
+    IN[i] = 0;
+    X[i] = hash_uniform(((unsigned long long)(z * 131071 + v) << 32) ^ (unsigned long long)i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {      // dlagtf
+    double tolmax = 0.0;
+    double scale1 = fabs(A[0]) + fabs(B[0]);
+    for (int k = 0; k < n - 1; ++k) {
+      double ak = A[k], ak1 = A[k + 1];
+      const double bk = B[k], ck = C[k];
+      const double bk1 = (k < n - 2) ? B[k + 1] : 0.0;
+      double scale2 = fabs(ck) + fabs(ak1);
+      if (k < n - 2) scale2 += fabs(bk1);
+      const double piv1 = (ak == 0.0) ? 0.0 : fabs(ak) / scale1;
+      if (ck == 0.0) {
+        scale1 = scale2;
+      } else {
+        const double piv2 = fabs(ck) / scale2;
+        if (piv2 <= piv1) {
+          scale1 = scale2;
+          const double m = ck / ak;
+          C[k] = m;
+          A[k + 1] = ak1 - m * bk;
+        } else {
+          IN[k] = 1;
+          const double mult = ak / ck;
+          A[k] = ck;
+          A[k + 1] = bk - mult * ak1;
+          if (k < n - 2) {
+            D2[k] = bk1;
+            B[k + 1] = -mult * bk1;
+          }
+          B[k] = ak1;
+          C[k] = mult;
+        }
+      }
+      tolmax = fmax(tolmax, fmax(fabs(A[k]), fmax(fabs(B[k]), fabs(D2[k]))));
+    }
+    tolmax = fmax(tolmax, fabs(A[n - 1]));
+    double tol = tolmax * eps;
+    if (tol == 0.0) tol = eps;
+    sh[0] = tol;
+    sh[1] = A[n - 1];
+  }
+  __syncthreads();
+  const double tol = sh[0], alast = sh[1];
+  const double sfmin = DBL_MIN, bignum = 1.0 / DBL_MIN;
+  const double dtpcrt = sqrt(0.1 / n);
+  int nrmchk = 0, its = 0;
+  bool ok = false;
+  while (its < 8) {
+    ++its;
+    double xm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xm = fmax(xm, fabs(X[i]));
+    xm = block_max128(xm, red);
+    const double scl = n * onenrm * fmax(eps, fabs(alast)) / xm;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) X[i] *= scl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // forward elimination (dlagts job = -1)
+      for (int k = 1; k < n; ++k) {
+        if (IN[k - 1] == 0) X[k] -= C[k - 1] * X[k - 1];
+        else {
+          const double t = X[k - 1];
+          X[k - 1] = X[k];
+          X[k] = t - C[k - 1] * X[k];
+        }
+      }
+      // back substitution with pivot perturbation
+      for (int k = n - 1; k >= 0; --k) {
+        double temp = X[k];
+        if (k <= n - 3) temp = temp - B[k] * X[k + 1] - D2[k] * X[k + 2];
+        else if (k == n - 2) temp = temp - B[k] * X[k + 1];
+        double akk = A[k];
+        double pert = copysign(tol, akk);
+        for (;;) {
+          const double absak = fabs(akk);
+          if (absak < 1.0) {
+            if (absak < sfmin) {
+              if (absak == 0.0 || fabs(temp) * sfmin > absak) { akk += pert; pert *= 2.0; continue; }
+              temp *= bignum; akk *= bignum;
+            } else if (fabs(temp) > absak * bignum) { akk += pert; pert *= 2.0; continue; }
+          }
+          break;
+        }
+        X[k] = temp / akk;
+      }
+    }
+    __syncthreads();
+    double nrm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) nrm = fmax(nrm, fabs(X[i]));
+    nrm = block_max128(nrm, red);
+    if (nrm < dtpcrt) continue;
+    if (++nrmchk < 3) continue;
+    ok = true;
+    break;
+  }
+  if (!ok && threadIdx.x == 0) atomicOr(&info[z * 4 + 1], 1);
+  double ss = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ss = fma(X[i], X[i], ss);
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const double inv = 1.0 / sqrt(red[0] + red[1] + red[2] + red[3]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) Xout[(size_t)i * Vp] = X[i] * inv;
+}
+
 // Re-orthogonalise eigenvectors whose eigenvalues are (nearly) degenerate: modified Gram-Schmidt inside each
 // run of consecutive eigenvalues closer than ctol * |T|.  One CTA per zone.
 __global__ void __launch_bounds__(256) eig_cluster_mgs_kernel(const double* __restrict__ lam,
@@ -407,38 +564,130 @@ __global__ void __launch_bounds__(256) eig_cluster_mgs_kernel(const double* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// q = H_0 H_1 ... H_{n-3} z  (apply reflectors in reverse order), one CTA per eigenvector.  grid (V, nz).
-__global__ void __launch_bounds__(256) eig_backtransform_kernel(const double* __restrict__ iv,
+// Back-transformation q = Q z = H_0 H_1 ... H_{n-2} z with the reflectors grouped in blocks of WYB:
+// H_{j0} ... H_{j0+WYB-1} = I - V T V^T (compact WY, LAPACK dlarft forward/columnwise).
+// (1) wy_tfactor_kernel: one CTA per block forms the Gram matrix V^T V and T.   grid (ceil(n/WYB), nz)
+constexpr int WYB = 8;
+constexpr int BTT = 1024;   // threads of the back-transformation / back-solve CTAs
+
+__global__ void __launch_bounds__(256) wy_tfactor_kernel(const double* __restrict__ VH, const double* __restrict__ tau,
+                                                         double* __restrict__ Tf, int n, int ldn) {
+  __shared__ double G[WYB][WYB];
+  __shared__ double red[8][WYB * (WYB + 1) / 2];
+  const int blk = blockIdx.x, z = blockIdx.y, j0 = blk * WYB;
+  const int nb = min(WYB, n - j0);
+  const double* vh = VH + (size_t)z * n * ldn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[WYB * (WYB + 1) / 2];
+#pragma unroll
+  for (int p = 0; p < WYB * (WYB + 1) / 2; ++p) acc[p] = 0.0;
+  for (int i = j0 + 1 + threadIdx.x; i < n; i += blockDim.x) {
+    double v[WYB];
+#pragma unroll
+    for (int c = 0; c < WYB; ++c) v[c] = (c < nb) ? vh[(size_t)(j0 + c) * ldn + i] : 0.0;
+    int p = 0;
+#pragma unroll
+    for (int c = 0; c < WYB; ++c)
+#pragma unroll
+      for (int d = 0; d <= c; ++d) { acc[p] = fma(v[c], v[d], acc[p]); ++p; }
+  }
+#pragma unroll
+  for (int p = 0; p < WYB * (WYB + 1) / 2; ++p) {
+    const double t = warp_sum(acc[p]);
+    if (lane == 0) red[warp][p] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < WYB * (WYB + 1) / 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    int c = 0, p = threadIdx.x;
+    while (p > c) { p -= c + 1; ++c; }
+    G[c][p] = t;
+    G[p][c] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double T[WYB][WYB];
+    for (int c = 0; c < WYB; ++c)
+      for (int d = 0; d < WYB; ++d) T[c][d] = 0.0;
+    for (int i = 0; i < nb; ++i) {
+      const double ti = tau[(size_t)z * n + j0 + i];
+      T[i][i] = ti;
+      // T(0:i, i) = -tau_i * T(0:i, 0:i) * (V(:, 0:i)^T v_i)
+      for (int r = 0; r < i; ++r) {
+        double sacc = 0.0;
+        for (int k = r; k < i; ++k) sacc += T[r][k] * G[k][i];
+        T[r][i] = -ti * sacc;
+      }
+    }
+    double* out = Tf + ((size_t)z * gridDim.x + blk) * WYB * WYB;
+    for (int c = 0; c < WYB; ++c)
+      for (int d = 0; d < WYB; ++d) out[c * WYB + d] = T[c][d];
+  }
+}
+
+// (2) one CTA per eigenvector: z <- (I - V T V^T) z for the blocks in descending order; one barrier per block.
+__global__ void __launch_bounds__(BTT) eig_backtransform_kernel(const double* __restrict__ iv,
                                                                 const double* __restrict__ VH,
-                                                                const double* __restrict__ tau,
+                                                                const double* __restrict__ Tf,
                                                                 double* __restrict__ Zt, int n, int ldn, int V, int Vp) {
   extern __shared__ double xs[];
-  __shared__ double red[2][8];
+  __shared__ double red[2][BTT / 32][WYB];
   const int v = blockIdx.x, z = blockIdx.y;
   const double* X = iv + (size_t)z * 6 * n * Vp + 4 * (size_t)n * Vp + v;
   for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = X[(size_t)i * Vp];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* vh = VH + (size_t)z * n * ldn;
-  const double* tz = tau + (size_t)z * n;
+  const int nblk = (n + WYB - 1) / WYB;
+  const double* tf = Tf + (size_t)z * nblk * WYB * WYB;
   int par = 0;
-  for (int j = n - 2; j >= 0; --j) {
-    const double t = tz[j];
-    if (t == 0.0) continue;               // uniform across the CTA
-    const double* vj = vh + (size_t)j * ldn;
-    // fixed ownership i == threadIdx.x (mod 256) so xs needs no barrier between reflectors
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int j0 = blk * WYB;
+    // fixed ownership i == threadIdx.x (mod BTT) so xs needs no barrier between blocks
     int i0 = threadIdx.x;
-    if (i0 <= j) i0 += ((j - i0) / 256 + 1) * 256;
-    double s = 0.0;
-    for (int i = i0; i < n; i += 256) s = fma(vj[i], xs[i], s);
-    s = warp_sum(s);
-    if (lane == 0) red[par][warp] = s;
-    __syncthreads();
-    double tot = 0.0;
+    if (i0 <= j0) i0 += ((j0 - i0) / BTT + 1) * BTT;
+    double s[WYB];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[par][w];
-    tot *= t;
-    for (int i = i0; i < n; i += 256) xs[i] = fma(-tot, vj[i], xs[i]);
+    for (int c = 0; c < WYB; ++c) s[c] = 0.0;
+#pragma unroll 4
+    for (int i = i0; i < n; i += BTT) {
+      const double xi = xs[i];
+#pragma unroll
+      for (int c = 0; c < WYB; ++c)
+        if (j0 + c < n) s[c] = fma(vh[(size_t)(j0 + c) * ldn + i], xi, s[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < WYB; ++c) {
+      const double t = warp_sum(s[c]);
+      if (lane == 0) red[par][warp][c] = t;
+    }
+    __syncthreads();
+    double sv[WYB], tv[WYB];
+#pragma unroll
+    for (int c = 0; c < WYB; ++c) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < BTT / 32; ++w) t += red[par][w][c];
+      sv[c] = t;
+    }
+    const double* T = tf + (size_t)blk * WYB * WYB;
+#pragma unroll
+    for (int c = 0; c < WYB; ++c) {
+      double t = 0.0;
+#pragma unroll
+      for (int d = 0; d < WYB; ++d)
+        if (d >= c) t = fma(__ldg(T + c * WYB + d), sv[d], t);
+      tv[c] = t;
+    }
+#pragma unroll 4
+    for (int i = i0; i < n; i += BTT) {
+      double xi = xs[i];
+#pragma unroll
+      for (int c = 0; c < WYB; ++c)
+        if (j0 + c < n) xi = fma(-tv[c], vh[(size_t)(j0 + c) * ldn + i], xi);
+      xs[i] = xi;
+    }
     par ^= 1;
   }
   __syncthreads();
@@ -446,36 +695,39 @@ __global__ void __launch_bounds__(256) eig_backtransform_kernel(const double* __
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = xs[i];
 }
 
-// u = L^-T q for each eigenvector (back substitution, row-oriented), one CTA per vector.  grid (V, nz).
-__global__ void __launch_bounds__(256) eig_backsolve_kernel(const double* __restrict__ Lm, double* __restrict__ Zt,
-                                                            int n, int ldn, int V) {
+// u = L^-T q for each eigenvector, one CTA per vector.  The diagonal blocks are applied through their
+// precomputed inverses (Dinv from the Cholesky), the rest is a row-oriented update.  grid (V, nz).
+__global__ void __launch_bounds__(BTT) eig_backsolve_kernel(const double* __restrict__ Lm,
+                                                            const double* __restrict__ Dinv, double* __restrict__ Zt,
+                                                            int n, int ldn, int V, int nblk) {
   extern __shared__ double xs[];
-  __shared__ double us[32];
+  __shared__ double us[NB];
   const int v = blockIdx.x, z = blockIdx.y;
   double* q = Zt + ((size_t)z * V + v) * n;
   const double* L = Lm + (size_t)z * n * ldn;
+  const double* Di = Dinv + (size_t)z * nblk * NB * NB;
   for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = q[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b1 = n; b1 > 0; b1 -= 32) {
-    const int b0 = max(0, b1 - 32), bs = b1 - b0;
-    if (warp == 0) {
-      // triangular solve of the bs x bs diagonal block, lane r' owns xs[b0 + r']
-      double mine = lane < bs ? xs[b0 + lane] : 0.0;
-      for (int r = bs - 1; r >= 0; --r) {
-        const double num = __shfl_sync(0xffffffffu, mine, r);
-        const double ur = num / L[(size_t)(b0 + r) * ldn + b0 + r];
-        if (lane == r) mine = ur;
-        else if (lane < r) mine -= ur * L[(size_t)(b0 + r) * ldn + b0 + lane];
-      }
-      if (lane < bs) { xs[b0 + lane] = mine; us[lane] = mine; }
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int b0 = b * NB, bs = min(NB, n - b0);
+    // u_b = Linv_bb^T q_b :  u[c] = sum_{r >= c} Linv[r][c] q[r]   (4 threads per output)
+    if (threadIdx.x < 4 * NB) {            // warps 0..7
+      const int c = threadIdx.x >> 2, part = threadIdx.x & 3;
+      double acc = 0.0;
+      if (c < bs)
+        for (int r = c + part; r < bs; r += 4) acc = fma(Di[((size_t)b * NB + r) * NB + c], xs[b0 + r], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0 && c < bs) us[c] = acc;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < b0; c += blockDim.x) {
       double acc = 0.0;
+#pragma unroll 16
       for (int r = 0; r < bs; ++r) acc = fma(us[r], L[(size_t)(b0 + r) * ldn + c], acc);
       xs[c] -= acc;
     }
+    if (threadIdx.x < bs) xs[b0 + threadIdx.x] = us[threadIdx.x];
     __syncthreads();
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] = xs[i];
@@ -519,6 +771,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.wbuf, vec));
   APV_TRY(al((void**)&ws.tdws, tridiag_scratch_doubles(n, nz) * sizeof(double)));
   APV_TRY(al((void**)&ws.vcur, (size_t)nz * 2 * n * sizeof(double)));
+  APV_TRY(al((void**)&ws.Tf, (size_t)nz * ceil_div(n, WYB) * WYB * WYB * sizeof(double)));
   APV_TRY(al((void**)&ws.lam, (size_t)nz * V * sizeof(double)));
   APV_TRY(al((void**)&ws.shift, (size_t)nz * V * sizeof(double) + (size_t)nz * 4 * sizeof(double)));
   APV_TRY(al((void**)&ws.iv, (size_t)nz * 6 * n * ws.Vp * sizeof(double)));
@@ -534,7 +787,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
@@ -548,27 +801,45 @@ void jdiag_free(JdiagWs& ws) {
 }
 
 // X <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones.
+// X <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones.
+// Blocked forward substitution with delayed updates: inside a super-block of NSUB x NB rows the NB-row blocks are
+// solved with the precomputed diagonal-block inverses and rank-NB updates confined to the super-block; everything
+// below receives ONE rank-(NSUB NB) DMMA update, so the right-hand side is streamed n / (NSUB NB) times only.
 static int trsm_lower(JdiagWs& ws, double* X, int m, int ldx, long long strideX, cudaStream_t st, int* launches) {
   const int n = ws.n, ldn = ws.ldn, nblk = ceil_div(n, NB);
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nbk = std::min(NB, n - k0);
-    GemmArgs g{};
-    g.batch = ws.nz;
-    // X_k <- Linv_kk X_k (in place: one row tile, each CTA owns its columns)
-    g.A = ws.Dinv + (size_t)(k0 / NB) * NB * NB; g.lda = NB; g.strideA = (long long)nblk * NB * NB;
-    g.B = X + (size_t)k0 * ldx; g.ldb = ldx; g.strideB = strideX;
-    g.C = X + (size_t)k0 * ldx; g.ldc = ldx; g.strideC = strideX;
-    g.M = nbk; g.N = m; g.K = nbk; g.alpha = 1.0; g.beta = 0.0;
-    APV_TRY(gemm_f64(g, st));
-    ++*launches;
-    const int rem = n - k0 - nbk;
-    if (rem > 0) {
+  const long long mstride = (long long)n * ldn;
+  for (int s0 = 0; s0 < n; s0 += SB) {
+    const int s1 = std::min(n, s0 + SB);
+    for (int k0 = s0; k0 < s1; k0 += NB) {
+      const int nbk = std::min(NB, n - k0);
+      GemmArgs g{};
+      g.batch = ws.nz;
+      // X_k <- Linv_kk X_k (in place: one row tile, each CTA owns its columns)
+      g.A = ws.Dinv + (size_t)(k0 / NB) * NB * NB; g.lda = NB; g.strideA = (long long)nblk * NB * NB;
+      g.B = X + (size_t)k0 * ldx; g.ldb = ldx; g.strideB = strideX;
+      g.C = X + (size_t)k0 * ldx; g.ldc = ldx; g.strideC = strideX;
+      g.M = nbk; g.N = m; g.K = nbk; g.alpha = 1.0; g.beta = 0.0;
+      APV_TRY(gemm_f64(g, st));
+      ++*launches;
+      const int rem = s1 - k0 - nbk;            // rows of the super-block still to be solved
+      if (rem > 0) {
+        GemmArgs u{};
+        u.batch = ws.nz;
+        u.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; u.lda = ldn; u.strideA = mstride;
+        u.B = X + (size_t)k0 * ldx; u.ldb = ldx; u.strideB = strideX;
+        u.C = X + (size_t)(k0 + nbk) * ldx; u.ldc = ldx; u.strideC = strideX;
+        u.M = rem; u.N = m; u.K = nbk; u.alpha = -1.0; u.beta = 1.0;
+        APV_TRY(gemm_f64(u, st));
+        ++*launches;
+      }
+    }
+    if (s1 < n) {
       GemmArgs u{};
       u.batch = ws.nz;
-      u.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; u.lda = ldn; u.strideA = (long long)n * ldn;
-      u.B = X + (size_t)k0 * ldx; u.ldb = ldx; u.strideB = strideX;
-      u.C = X + (size_t)(k0 + nbk) * ldx; u.ldc = ldx; u.strideC = strideX;
-      u.M = rem; u.N = m; u.K = nbk; u.alpha = -1.0; u.beta = 1.0;
+      u.A = ws.Lm + (size_t)s1 * ldn + s0; u.lda = ldn; u.strideA = mstride;
+      u.B = X + (size_t)s0 * ldx; u.ldb = ldx; u.strideB = strideX;
+      u.C = X + (size_t)s1 * ldx; u.ldc = ldx; u.strideC = strideX;
+      u.M = n - s1; u.N = m; u.K = s1 - s0; u.alpha = -1.0; u.beta = 1.0;
       APV_TRY(gemm_f64(u, st));
       ++*launches;
     }
@@ -592,27 +863,44 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   const int nblk = ceil_div(n, NB);
   const size_t chol_smem = (size_t)2 * NB * (NB + 1) * sizeof(double);
   APV_TRY(ensure_smem(chol_diag_kernel, chol_smem));
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nbk = std::min(NB, n - k0);
-    chol_diag_kernel<<<nz, 256, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
-    ++nl;
-    const int rem = n - k0 - nbk;
-    if (rem > 0) {
-      GemmArgs p{};          // L21 = A21 * Linv11^T   (in place: one column tile)
-      p.batch = nz;
-      p.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.lda = ldn; p.strideA = mstride;
-      p.B = ws.Dinv + (size_t)(k0 / NB) * NB * NB; p.ldb = NB; p.strideB = (long long)nblk * NB * NB;
-      p.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.ldc = ldn; p.strideC = mstride;
-      p.M = rem; p.N = nbk; p.K = nbk; p.transB = 1; p.alpha = 1.0; p.beta = 0.0;
-      APV_TRY(gemm_f64(p, st));
-      GemmArgs u{};          // A22 -= L21 L21^T  (lower tiles)
+  for (int s0 = 0; s0 < n; s0 += SB) {
+    const int s1 = std::min(n, s0 + SB);
+    for (int k0 = s0; k0 < s1; k0 += NB) {
+      const int nbk = std::min(NB, n - k0);
+      chol_diag_kernel<<<nz, 256, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
+      ++nl;
+      const int below = n - k0 - nbk;
+      if (below > 0) {
+        GemmArgs p{};          // L[below, k] = A[below, k] * Linv_kk^T   (in place: one column tile)
+        p.batch = nz;
+        p.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.lda = ldn; p.strideA = mstride;
+        p.B = ws.Dinv + (size_t)(k0 / NB) * NB * NB; p.ldb = NB; p.strideB = (long long)nblk * NB * NB;
+        p.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.ldc = ldn; p.strideC = mstride;
+        p.M = below; p.N = nbk; p.K = nbk; p.transB = 1; p.alpha = 1.0; p.beta = 0.0;
+        APV_TRY(gemm_f64(p, st));
+        ++nl;
+        const int cols = s1 - k0 - nbk;      // remaining columns of the super-block
+        if (cols > 0) {
+          GemmArgs u{};        // A[below, sb cols] -= L[below, k] L[sb rows, k]^T
+          u.batch = nz;
+          u.A = p.C; u.lda = ldn; u.strideA = mstride;
+          u.B = p.C; u.ldb = ldn; u.strideB = mstride;
+          u.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0 + nbk; u.ldc = ldn; u.strideC = mstride;
+          u.M = below; u.N = cols; u.K = nbk; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+          APV_TRY(gemm_f64(u, st));
+          ++nl;
+        }
+      }
+    }
+    if (s1 < n) {
+      GemmArgs u{};            // trailing: A22 -= L[rest, sb] L[rest, sb]^T  (lower tiles), K = super-block width
       u.batch = nz;
-      u.A = p.C; u.lda = ldn; u.strideA = mstride;
-      u.B = p.C; u.ldb = ldn; u.strideB = mstride;
-      u.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0 + nbk; u.ldc = ldn; u.strideC = mstride;
-      u.M = rem; u.N = rem; u.K = nbk; u.transB = 1; u.tri = 1; u.alpha = -1.0; u.beta = 1.0;
+      u.A = ws.Lm + (size_t)s1 * ldn + s0; u.lda = ldn; u.strideA = mstride;
+      u.B = u.A; u.ldb = ldn; u.strideB = mstride;
+      u.C = ws.Lm + (size_t)s1 * ldn + s1; u.ldc = ldn; u.strideC = mstride;
+      u.M = n - s1; u.N = n - s1; u.K = s1 - s0; u.transB = 1; u.tri = 1; u.alpha = -1.0; u.beta = 1.0;
       APV_TRY(gemm_f64(u, st));
-      nl += 2;
+      ++nl;
     }
   }
 
@@ -635,14 +923,22 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   APV_TRY(ensure_smem(eig_bisect_kernel, (size_t)2 * n * sizeof(double)));
   eig_bisect_kernel<<<dim3(ceil_div(V, 8), nz), 256, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
   eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
-  eig_invit_kernel<<<dim3(ws.Vp / 32, nz), 32, 0, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
+  const size_t ivsm = (size_t)5 * n * sizeof(double) + (size_t)round_up(n, 16);
+  if (ivsm <= 200 * 1024) {
+    APV_TRY(ensure_smem(eig_invit_smem_kernel, ivsm));
+    eig_invit_smem_kernel<<<dim3(V, nz), 128, ivsm, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
+  } else {
+    eig_invit_kernel<<<dim3(ws.Vp / 32, nz), 32, 0, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
+  }
   eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
   APV_CUDA_TRY(cudaEventRecord(ws.ev[4], st));
   APV_TRY(ensure_smem(eig_backtransform_kernel, (size_t)n * sizeof(double)));
-  eig_backtransform_kernel<<<dim3(V, nz), 256, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.tau, ws.Zt, n, ldn, V, ws.Vp);
+  wy_tfactor_kernel<<<dim3(ceil_div(n, WYB), nz), 256, 0, st>>>(ws.VH, ws.tau, ws.Tf, n, ldn);
+  eig_backtransform_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.Tf, ws.Zt, n, ldn, V, ws.Vp);
+  ++nl;
   APV_CUDA_TRY(cudaEventRecord(ws.ev[5], st));
   APV_TRY(ensure_smem(eig_backsolve_kernel, (size_t)n * sizeof(double)));
-  eig_backsolve_kernel<<<dim3(V, nz), 256, (size_t)n * sizeof(double), st>>>(ws.Lm, ws.Zt, n, ldn, V);
+  eig_backsolve_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.Lm, ws.Dinv, ws.Zt, n, ldn, V, nblk);
   nl += 6;
   APV_CUDA_TRY(cudaEventRecord(ws.ev[6], st));
   APV_CUDA_TRY(cudaGetLastError());
