@@ -67,7 +67,7 @@ class apvast:
                  reference_index_A: int, reference_index_B: int, number_of_eigenvectors: int, mu: float,
                  statistics_buffer_length: int, hop_size: int = None, sampling_rate: int = 48000,
                  run_A: bool = True, run_B: bool = True, perceptual: bool = True, *, model=None,
-                 device: int = None, eig_mode: int = 0):
+                 device: int = None, eig_mode: int = 0, stats_mode: int = 0):
         self._h = None
         self.block_size = int(block_size)
         self.rir_A = rir_A
@@ -124,7 +124,7 @@ class apvast:
             n_eig=self.number_of_eigenvectors, modeling_delay=self.modeling_delay,
             ref_A=self.reference_index_A, ref_B=self.reference_index_B, run_A=int(self.run_A), run_B=int(self.run_B),
             perceptual=mode, normalize_gains=int(bool(EXPERIMENTAL_NORMALIZE_GAINS)), eig_mode=int(eig_mode),
-            stats_mode=0, device=-1 if device is None else int(device), mu=self._mu, reg=1e-7,
+            stats_mode=int(stats_mode), device=-1 if device is None else int(device), mu=self._mu, reg=1e-7,
             sampling_rate=float(sampling_rate))
         h = C.c_void_p()
         capi.check(capi.lib().apv_create(C.byref(cfg), capi.ptr(rA), capi.ptr(rB), capi.ptr(init), C.byref(h)))

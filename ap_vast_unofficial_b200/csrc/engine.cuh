@@ -81,6 +81,7 @@ struct Handle {
   double* S = nullptr;       // [4][M][L][N]
   double* ST = nullptr;      // [2][M][N]
   double* Sp = nullptr;      // [4][M][L][Ns]   s' = delete(S, J), zero padded
+  double* seed = nullptr;    // [4][L][L][J]    first-row correlations (stats_mode 2)
   double* Wg = nullptr;      // [2][M][F]
   double* tframe = nullptr;  // [2][M][Nb]
   double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)

@@ -183,6 +183,121 @@ __global__ void __launch_bounds__(256) rvec_kernel(const double* __restrict__ Sp
   if (lane == 0) rvec[(size_t)X * D.n + r] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// stats_mode 2: structured evaluation.  Inside a loudspeaker pair (l, l') the statistics are correlations of
+// sliding windows, c(q, q') = sum_m sum_{p<P} a_l[q+p] a_l'[q'+p]  (q = J-1-i), and obey
+//     c(q+1, q'+1) = c(q, q') - sum_m a_l[q] a_l'[q'] + sum_m a_l[q+P] a_l'[q'+P].
+// Only the first row c(0, q') of every pair is summed directly (L^2 J correlations of M P terms instead of
+// L^2 J^2); every other entry follows along its diagonal.  The recurrence runs in double-double arithmetic
+// (error-free products/sums), so an entry carries the rounding of its directly summed seed only.
+// This is ~J/2 times fewer flops than the SYRK; it is an opt-in alternative to the tensor-core kernel above.
+
+// seed[path][l][l'][q'] = c_{l l'}(0, q').   grid (L, L, 4), blockDim = 256; thread per q'.
+__global__ void __launch_bounds__(256) stats_seed_kernel(const double* __restrict__ Sp, double* __restrict__ seed,
+                                                         Dims D, unsigned path_mask) {
+  extern __shared__ double sm[];
+  const int lp = blockIdx.x, l = blockIdx.y, path = blockIdx.z;
+  if (!((path_mask >> path) & 1u)) return;
+  const int J = D.J, P = D.P;
+  double* al = sm;             // a_l[0 .. P)
+  double* ap = sm + P;         // a_l'[0 .. P + J - 1)
+  const int nq = (J + 255) / 256;
+  double acc[4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+  for (int m = 0; m < D.M; ++m) {
+    const double* sl = Sp + (((size_t)path * D.M + m) * D.L + l) * D.Ns;
+    const double* sp = Sp + (((size_t)path * D.M + m) * D.L + lp) * D.Ns;
+    __syncthreads();
+    for (int e = threadIdx.x; e < P; e += 256) al[e] = sl[e];
+    for (int e = threadIdx.x; e < P + J - 1; e += 256) ap[e] = sp[e];
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < nq) {
+        const int q = min(threadIdx.x + 256 * u, J - 1);
+        const double* b = ap + q;
+        double a0 = acc[u][0], a1 = acc[u][1];
+        int p = 0;
+        for (; p + 1 < P; p += 2) {
+          a0 = fma(al[p], b[p], a0);
+          a1 = fma(al[p + 1], b[p + 1], a1);
+        }
+        if (p < P) a0 = fma(al[p], b[p], a0);
+        acc[u][0] = a0;
+        acc[u][1] = a1;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int q = threadIdx.x + 256 * u;
+    if (u < nq && q < J) seed[(((size_t)path * D.L + l) * D.L + lp) * J + q] = acc[u][0] + acc[u][1];
+  }
+}
+
+__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double x, double y, double sign) {
+  double p = x * y;
+  double e = fma(x, y, -p);
+  p *= sign;
+  e *= sign;
+  const double s = hi + p;
+  const double bb = s - hi;
+  const double err = (hi - (s - bb)) + (p - bb);
+  hi = s;
+  lo += err + e;
+}
+
+// Diagonal walk.  grid (L, L, 4); thread t walks the diagonal q' - q = t of pair (l, l'): entries (k, t + k).
+// Writes R[(l, J-1-k), (l', J-1-t-k)] (coalesced over t).
+__global__ void __launch_bounds__(256) stats_recur_kernel(const double* __restrict__ Sp, const double* __restrict__ seed,
+                                                          double* __restrict__ R, Dims D, unsigned path_mask) {
+  const int lp = blockIdx.x, l = blockIdx.y, path = blockIdx.z;
+  if (!((path_mask >> path) & 1u)) return;
+  const int J = D.J, P = D.P, M = D.M;
+  double* Rp = R + (size_t)path * D.n * D.ldn;
+  const size_t ms = (size_t)D.L * D.Ns;                       // microphone stride
+  const double* sl = Sp + ((size_t)path * M * D.L + l) * D.Ns;
+  const double* sp = Sp + ((size_t)path * M * D.L + lp) * D.Ns;
+  for (int t = threadIdx.x; t < J; t += blockDim.x) {
+    double hi = seed[(((size_t)path * D.L + l) * D.L + lp) * J + t], lo = 0.0;
+    for (int k = 0; k + t < J; ++k) {
+      Rp[(size_t)(l * J + J - 1 - k) * D.ldn + lp * J + J - 1 - t - k] = hi + lo;
+      if (k + t + 1 < J) {
+        for (int m = 0; m < M; ++m) {
+          const double* a = sl + m * ms;
+          const double* b = sp + m * ms;
+          dd_add_prod(hi, lo, __ldg(a + k), __ldg(b + t + k), -1.0);
+          dd_add_prod(hi, lo, __ldg(a + k + P), __ldg(b + t + k + P), 1.0);
+        }
+        const double s2 = hi + lo;                            // renormalise
+        lo = lo - (s2 - hi);
+        hi = s2;
+      }
+    }
+  }
+}
+
+// Fill the entries the diagonal walk does not write: inside every J x J block the half with i' > i is the
+// transpose of an entry that was written (R is symmetric).  32 x 32 tiles through shared memory.
+__global__ void stats_mirror_kernel(double* __restrict__ R, Dims D, unsigned path_mask) {
+  __shared__ double t[32][33];
+  const int path = blockIdx.z;
+  if (!((path_mask >> path) & 1u)) return;
+  double* Rp = R + (size_t)path * D.n * D.ldn;
+  const int n = D.n, J = D.J;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;               // transposed tile
+    t[r][threadIdx.x] = (i < n && j < n) ? Rp[(size_t)i * D.ldn + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    if (i < n && j < n && (j % J) > (i % J)) Rp[(size_t)i * D.ldn + j] = t[threadIdx.x][r];
+  }
+}
+
 }  // namespace
 
 int stage_stats(Handle& h) {
@@ -204,6 +319,24 @@ int stage_stats(Handle& h) {
   }
   unsigned pmask = (D.runA ? 0x3u : 0u) | (D.runB ? 0xCu : 0u);
   unsigned zmask = (D.runA ? 1u : 0u) | (D.runB ? 2u : 0u);
+  if (h.cfg.stats_mode == 2) {
+    if (D.J > 1024) return EINVAL_;
+    const size_t ssm = (size_t)(2 * D.P + D.J) * sizeof(double);
+    static thread_local size_t conf2 = 0;
+    if (ssm > 48 * 1024 && ssm > conf2) {
+      APV_CUDA_TRY(cudaFuncSetAttribute(stats_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      conf2 = ssm;
+    }
+    APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[0], h.st));
+    stats_seed_kernel<<<dim3(D.L, D.L, 4), 256, ssm, h.st>>>(h.Sp, h.seed, D, pmask);
+    stats_recur_kernel<<<dim3(D.L, D.L, 4), 256, 0, h.st>>>(h.Sp, h.seed, h.R, D, pmask);
+    stats_mirror_kernel<<<dim3(ceil_div(D.n, 32), ceil_div(D.n, 32), 4), dim3(32, 8), 0, h.st>>>(h.R, D, pmask);
+    APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
+    rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
+    h.launches += 5;
+    APV_CUDA_TRY(cudaGetLastError());
+    return OK;
+  }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[0], h.st));
   syrk_toeplitz_kernel<<<dim3(ntile, 4), 256, sm, h.st>>>(h.Sp, h.R, D, ntile, SEG, maxl, pmask);
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));

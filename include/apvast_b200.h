@@ -51,7 +51,9 @@ typedef struct apv_config {
   int32_t normalize_gains;   /* EXPERIMENTAL_NORMALIZE_GAINS (:6,322-324)                           */
   int32_t eig_mode;          /* 0 auto; 1 tridiagonal + bisection + inverse iteration (top-V);
                                 2 cyclic Jacobi (small n, full spectrum)                            */
-  int32_t stats_mode;        /* 0 auto; 1 FP64 tensor-core SYRK with implicit Toeplitz operand      */
+  int32_t stats_mode;        /* 0/1 FP64 tensor-core SYRK with implicit Toeplitz operand (default);
+                                2 structured evaluation: first-row correlations + double-double
+                                  diagonal recurrence (~J/2 x fewer flops, opt-in)                  */
   int32_t device;            /* CUDA device ordinal, -1 = current                                   */
   double mu;                 /* (:49)                                                               */
   double reg;                /* absolute diagonal loading inside jdiag, reference 1e-7 (:22-24)     */

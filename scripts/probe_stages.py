@@ -19,7 +19,7 @@ def main():
         wl = make_workload(name)
         np.random.seed(0)
         t0 = time.time()
-        eng = apvast(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **wl["cfg"])
+        eng = apvast(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, stats_mode=int(os.environ.get("APV_STATS_MODE", "0")), **wl["cfg"])
         print(name, "create %.2fs" % (time.time() - t0))
         H = eng.hop_size
         for t in range(6):

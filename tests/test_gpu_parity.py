@@ -42,6 +42,13 @@ def test_golden_cfg1():
     _check(res, "cfg1")
 
 
+@pytest.mark.parametrize("name", ["tiny_hop", "mid", "cfg1"])
+def test_golden_structured_statistics(name):
+    """stats_mode=2 (first-row correlations + double-double diagonal recurrence) against the same golden vectors."""
+    eng, g, res = replay(_engine(), name, extra_ctor=dict(stats_mode=2))
+    _check(res, name + "-structured")
+
+
 def test_golden_full_rank_closed_form():
     """V = n: per-rank filters inside a degenerate eigenvalue cluster are basis-dependent (sign/rotation
     ambiguity, as for eigenvectors), so ranks are compared only where the eigenvalue gap is resolved; the
