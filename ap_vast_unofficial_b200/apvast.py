@@ -380,3 +380,12 @@ class apvast:
         for t, a in state.items():
             self._set(int(t), a)
         self._blocks = max(self._blocks, 1)
+
+    def save_state(self, path):
+        """Checkpoint the streaming state to an .npz file (the reference's closest facility is the property dump
+        of Python/make_python_test.m:19-24,55-64)."""
+        np.savez(path, **{f"t{t}": a for t, a in self.get_state().items()})
+
+    def load_state(self, path):
+        z = np.load(path)
+        self.set_state({int(k[1:]): z[k] for k in z.files})

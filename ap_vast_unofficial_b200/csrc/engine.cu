@@ -246,6 +246,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->Sp, 4 * M * L * (size_t)D.Ns));
   TRYB(dalloc(&h->Wg, 2 * M * (size_t)D.F));
   TRYB(dalloc(&h->seed, 4 * L * L * (size_t)D.J));
+  if (cfg->stats_mode != 2) TRYB(dalloc(&h->Pbuf, 16 * n * (size_t)D.ldn));
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
   TRYB(dalloc(&h->G, 2 * V * L * Nb));
   TRYB(dalloc(&h->Gt, 2 * Nb));
@@ -318,7 +319,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
 void apv_destroy(apv_handle* h) {
   if (!h) return;
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
-                h->Wg, h->seed, h->tframe, h->tspec, h->G, h->Gt, h->R, h->rvec, h->lam, h->U, h->W, h->d_in, h->d_out,
+                h->Wg, h->seed, h->Pbuf, h->tframe, h->tspec, h->G, h->Gt, h->R, h->rvec, h->lam, h->U, h->W, h->d_in, h->d_out,
                 h->d_out_t};
   for (void* p : ps)
     if (p) cudaFree(p);

@@ -82,6 +82,7 @@ struct Handle {
   double* ST = nullptr;      // [2][M][N]
   double* Sp = nullptr;      // [4][M][L][Ns]   s' = delete(S, J), zero padded
   double* seed = nullptr;    // [4][L][L][J]    first-row correlations (stats_mode 2)
+  double* Pbuf = nullptr;    // [4 slices][4][n][ldn] per-microphone partial statistics (DMMA SYRK, tree-summed)
   double* Wg = nullptr;      // [2][M][F]
   double* tframe = nullptr;  // [2][M][Nb]
   double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)

@@ -42,55 +42,93 @@ __global__ void prep_kernel(Ptr2 bright, Ptr2 dark, int ld_in, double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky of one diagonal block (<= NB x NB) in shared memory + its inverse.  grid (nz).
+// Cholesky of one diagonal block (<= NB x NB) and the inverse of its factor.  grid (nz), 256 threads.
+// The lower triangle lives in registers: thread t owns row r = t/4 and the columns c = (t%4) + 4q <= r.
+// Right-looking elimination with two barriers per column (pivot; scaled column), then the inverse by the same
+// elimination applied to the identity (L X = I, one row of X final per step).
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ Lm, double* __restrict__ Dinv, int n,
                                                         int ldn, int k0, int nbk, int nblk, int* __restrict__ info) {
-  extern __shared__ double chol_sm[];
-  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(chol_sm);
-  double (*Iv)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(chol_sm + NB * (NB + 1));
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double colj[NB];
+  __shared__ double xrow[NB];
   const int z = blockIdx.x, tid = threadIdx.x;
+  const int r = tid >> 2, cg = tid & 3;
   double* A = Lm + (size_t)z * n * ldn + (size_t)k0 * ldn + k0;
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e / NB, j = e % NB;
-    As[i][j] = (i < nbk && j < nbk && j <= i) ? A[(size_t)i * ldn + j] : 0.0;
-    Iv[i][j] = 0.0;
+  double a[NB / 4];
+#pragma unroll
+  for (int q = 0; q < NB / 4; ++q) {
+    const int c = cg + 4 * q;
+    a[q] = (c <= r) ? ((r < nbk && c < nbk) ? A[(size_t)r * ldn + c] : (r == c ? 1.0 : 0.0)) : 0.0;
   }
-  __syncthreads();
-  for (int j = 0; j < nbk; ++j) {
-    if (tid == 0) {
-      double d = As[j][j];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (r == j && cg == (j & 3)) {
+      double d = a[j >> 2];
       if (!(d > 0.0)) {                       // also catches NaN
-        if (info[z * 4] == 0) info[z * 4] = k0 + j + 1;
+        if (j < nbk && info[z * 4] == 0) info[z * 4] = k0 + j + 1;
         d = 1.0;
       }
-      As[j][j] = sqrt(d);
+      d = sqrt(d);
+      a[j >> 2] = d;
+      colj[j] = d;
     }
     __syncthreads();
-    const double dj = As[j][j];
-    for (int i = j + 1 + tid; i < nbk; i += blockDim.x) As[i][j] /= dj;
-    __syncthreads();
-    const int m = nbk - j - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int i = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= i) As[i][c] -= As[i][j] * As[c][j];
+    if (cg == (j & 3) && r > j) {
+      const double l = a[j >> 2] / colj[j];
+      a[j >> 2] = l;
+      colj[r] = l;
     }
     __syncthreads();
+    if (r > j) {
+      const double lr = colj[r];
+#pragma unroll
+      for (int q = 0; q < NB / 4; ++q) {
+        const int c = cg + 4 * q;
+        if (c > j && c <= r) a[q] = fma(-lr, colj[c], a[q]);
+      }
+    }
   }
-  // inverse of the lower-triangular block, one column per thread
-  if (tid < nbk) {
-    const int c = tid;
-    for (int i = c; i < nbk; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) s -= As[i][k] * Iv[k][c];
-      Iv[i][c] = s / As[i][i];
-    }
+  // factor -> shared + global (zeros above the diagonal)
+#pragma unroll
+  for (int q = 0; q < NB / 4; ++q) {
+    const int c = cg + 4 * q;
+    Ls[r][c] = (c <= r) ? a[q] : 0.0;
+    if (r < nbk && c < nbk) A[(size_t)r * ldn + c] = (c <= r) ? a[q] : 0.0;
   }
   __syncthreads();
+  // inverse: x holds the running right-hand side rows of L X = I
+  double x[NB / 4];
+#pragma unroll
+  for (int q = 0; q < NB / 4; ++q) x[q] = (cg + 4 * q == r) ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (r == j) {
+      const double inv = 1.0 / Ls[j][j];
+#pragma unroll
+      for (int q = 0; q < NB / 4; ++q) {
+        const int c = cg + 4 * q;
+        if (c <= j) {
+          x[q] *= inv;
+          xrow[c] = x[q];
+        }
+      }
+    }
+    __syncthreads();
+    if (r > j) {
+      const double lrj = Ls[r][j];
+#pragma unroll
+      for (int q = 0; q < NB / 4; ++q) {
+        const int c = cg + 4 * q;
+        if (c <= j) x[q] = fma(-lrj, xrow[c], x[q]);
+      }
+    }
+    __syncthreads();
+  }
   double* Di = Dinv + ((size_t)z * nblk + k0 / NB) * NB * NB;
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e / NB, j = e % NB;
-    Di[e] = Iv[i][j];
-    if (i < nbk && j < nbk) A[(size_t)i * ldn + j] = As[i][j];   // lower factor, zeros above the diagonal
+#pragma unroll
+  for (int q = 0; q < NB / 4; ++q) {
+    const int c = cg + 4 * q;
+    Di[r * NB + c] = (c <= r && r < nbk && c < nbk) ? x[q] : 0.0;
   }
 }
 
@@ -861,8 +899,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
 
   // ---- blocked Cholesky of Lm (lower)
   const int nblk = ceil_div(n, NB);
-  const size_t chol_smem = (size_t)2 * NB * (NB + 1) * sizeof(double);
-  APV_TRY(ensure_smem(chol_diag_kernel, chol_smem));
+  const size_t chol_smem = 0;
   for (int s0 = 0; s0 < n; s0 += SB) {
     const int s1 = std::min(n, s0 + SB);
     for (int k0 = s0; k0 < s1; k0 += NB) {

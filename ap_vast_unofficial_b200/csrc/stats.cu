@@ -9,6 +9,8 @@
 // buffered) and the FP64 tensor-core fragments (mma.sync m8n8k4 = SASS DMMA.8x8x4) are gathered
 // from them by index arithmetic: A[row][k] = seg[(J-1-i) + k].  Only lower-triangle tiles are
 // computed; the epilogue mirrors them so R is stored as a full symmetric matrix.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace apv {
@@ -36,10 +38,16 @@ __global__ void pack_stats_kernel(const double* __restrict__ S, double* __restri
 // Shared memory per stage: for the row side  nlr segments of SEG doubles, for the column side nlc segments,
 // plus one zero segment used by out-of-range rows.
 __global__ void __launch_bounds__(256, 1)
-syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ R, Dims D, int ntile, int SEG, int maxl,
-                     unsigned path_mask) {
+syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, Dims D, int ntile, int SEG, int maxl,
+                     unsigned path_mask, int m_first, int m_count) {
+  // blockIdx.z = microphone slice: the K dimension (microphones x P) is split per microphone and the per-microphone
+  // partial matrices are added up by a tree (syrk_reduce_kernel) -- a fixed-order accumulation over all M P terms
+  // would leave R with ~1e-14 relative rounding error, which the ill-conditioned pencil amplifies beyond the
+  // 1e-8 filter-parity bar at n = 4096.
   const int path = blockIdx.y;
   if (!((path_mask >> path) & 1u)) return;
+  const int mslice = blockIdx.z;
+  if (mslice >= m_count) return;
   // decode linear lower-triangle tile index -> (bi, bj), bi >= bj
   int t = blockIdx.x, bi = 0;
   while (t >= bi + 1) { t -= bi + 1; ++bi; }
@@ -87,14 +95,14 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ R, Dims
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int nchunk = (P + KC - 1) / KC;
-  const int nit = D.M * nchunk;
+  const int nit = nchunk;                                       // one microphone per CTA
   const size_t chan_stride = (size_t)D.Ns;
-  const double* base = Sp + (size_t)path * D.M * L * chan_stride;
+  const double* base = Sp + ((size_t)path * D.M + m_first + mslice) * L * chan_stride;
 
   auto stage_load = [&](int it, int s) {
-    const int m = it / nchunk, p0 = (it - m * nchunk) * KC;
+    const int p0 = it * KC;
     double* dst = sm + s * stage_sz;
-    const double* src = base + (size_t)m * L * chan_stride + p0;
+    const double* src = base + p0;
     const int tot_r = nlr * SEG;
     for (int e = tid; e < tot_r; e += 256) {
       const int ls = e / SEG, o = e - ls * SEG;
@@ -138,27 +146,49 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ R, Dims
     }
   }
 
-  double* Rp = R + (size_t)path * n * D.ldn;
+  // partial matrix of this microphone: lower triangle only (the reduction mirrors it)
+  double* Pp = Pbuf + ((size_t)mslice * 4 + path) * n * D.ldn;
 #pragma unroll
   for (int rt = 0; rt < 8; ++rt) {
     const int r = r0 + wm + rt * 8 + gq;
     if (r >= n) continue;
 #pragma unroll
     for (int ct = 0; ct < 4; ++ct) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = c0 + wn + ct * 8 + 2 * tq + u;
-        if (c >= n) continue;
-        const double v = acc[rt][ct][u];
-        if (bi != bj) {
-          Rp[(size_t)r * D.ldn + c] = v;
-          Rp[(size_t)c * D.ldn + r] = v;
-        } else if (r >= c) {          // diagonal tile: keep the lower half and mirror it (exactly symmetric)
-          Rp[(size_t)r * D.ldn + c] = v;
-          Rp[(size_t)c * D.ldn + r] = v;
-        }
+      const int c = c0 + wn + ct * 8 + 2 * tq;
+      if (c + 1 < n && (bi != bj || r >= c + 1)) {
+        *reinterpret_cast<double2*>(Pp + (size_t)r * D.ldn + c) = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
+      } else {
+        if (c < n && r >= c) Pp[(size_t)r * D.ldn + c] = acc[rt][ct][0];
+        if (c + 1 < n && r >= c + 1) Pp[(size_t)r * D.ldn + c + 1] = acc[rt][ct][1];
       }
     }
+  }
+}
+
+// R (+)= tree sum of the per-microphone partial matrices of one group; the last group also mirrors the lower
+// triangle so that R is stored as a full symmetric matrix.  grid (lower tiles, 4 paths), 256 threads.
+__global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* __restrict__ Pbuf, double* __restrict__ R, Dims D,
+                                                          unsigned path_mask, int m_count, int first, int last) {
+  const int path = blockIdx.y;
+  if (!((path_mask >> path) & 1u)) return;
+  int t = blockIdx.x, bi = 0;
+  while (t >= bi + 1) { t -= bi + 1; ++bi; }
+  const int bj = t;
+  const int n = D.n, ldn = D.ldn;
+  const size_t ps = (size_t)4 * n * ldn;                        // slice stride
+  const double* P0 = Pbuf + (size_t)path * n * ldn;
+  double* Rp = R + (size_t)path * n * ldn;
+  for (int e = threadIdx.x; e < TM * TM; e += 256) {
+    const int r = bi * TM + e / TM, c = bj * TM + (e % TM);
+    if (r >= n || c >= n || c > r) continue;
+    const size_t o = (size_t)r * ldn + c;
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = q < m_count ? P0[q * ps + o] : 0.0;
+    double s = (v[0] + v[1]) + (v[2] + v[3]);
+    if (!first) s += Rp[o];
+    Rp[o] = s;
+    if (last && c != r) Rp[(size_t)c * ldn + r] = s;
   }
 }
 
@@ -192,7 +222,21 @@ __global__ void __launch_bounds__(256) rvec_kernel(const double* __restrict__ Sp
 // (error-free products/sums), so an entry carries the rounding of its directly summed seed only.
 // This is ~J/2 times fewer flops than the SYRK; it is an opt-in alternative to the tensor-core kernel above.
 
-// seed[path][l][l'][q'] = c_{l l'}(0, q').   grid (L, L, 4), blockDim = 256; thread per q'.
+__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double x, double y, double sign) {
+  double p = x * y;
+  double e = fma(x, y, -p);
+  p *= sign;
+  e *= sign;
+  const double s = hi + p;
+  const double bb = s - hi;
+  const double err = (hi - (s - bb)) + (p - bb);
+  hi = s;
+  lo += err + e;
+}
+
+// seed[path][l][l'][q'] = c_{l l'}(0, q'), summed in double-double (error-free products and sums) so that the
+// seeds -- and with them every entry of R -- are correct to about one ulp.   grid (L, L, 4), blockDim = 256;
+// thread per q'.
 __global__ void __launch_bounds__(256) stats_seed_kernel(const double* __restrict__ Sp, double* __restrict__ seed,
                                                          Dims D, unsigned path_mask) {
   extern __shared__ double sm[];
@@ -202,9 +246,9 @@ __global__ void __launch_bounds__(256) stats_seed_kernel(const double* __restric
   double* al = sm;             // a_l[0 .. P)
   double* ap = sm + P;         // a_l'[0 .. P + J - 1)
   const int nq = (J + 255) / 256;
-  double acc[4][2];
+  double hi[4], lo[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+  for (int u = 0; u < 4; ++u) hi[u] = lo[u] = 0.0;
   for (int m = 0; m < D.M; ++m) {
     const double* sl = Sp + (((size_t)path * D.M + m) * D.L + l) * D.Ns;
     const double* sp = Sp + (((size_t)path * D.M + m) * D.L + lp) * D.Ns;
@@ -217,35 +261,19 @@ __global__ void __launch_bounds__(256) stats_seed_kernel(const double* __restric
       if (u < nq) {
         const int q = min(threadIdx.x + 256 * u, J - 1);
         const double* b = ap + q;
-        double a0 = acc[u][0], a1 = acc[u][1];
-        int p = 0;
-        for (; p + 1 < P; p += 2) {
-          a0 = fma(al[p], b[p], a0);
-          a1 = fma(al[p + 1], b[p + 1], a1);
-        }
-        if (p < P) a0 = fma(al[p], b[p], a0);
-        acc[u][0] = a0;
-        acc[u][1] = a1;
+        double h = hi[u], w = lo[u];
+        for (int p = 0; p < P; ++p) dd_add_prod(h, w, al[p], b[p], 1.0);
+        const double s2 = h + w;          // renormalise once per microphone
+        lo[u] = w - (s2 - h);
+        hi[u] = s2;
       }
     }
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int q = threadIdx.x + 256 * u;
-    if (u < nq && q < J) seed[(((size_t)path * D.L + l) * D.L + lp) * J + q] = acc[u][0] + acc[u][1];
+    if (u < nq && q < J) seed[(((size_t)path * D.L + l) * D.L + lp) * J + q] = hi[u] + lo[u];
   }
-}
-
-__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double x, double y, double sign) {
-  double p = x * y;
-  double e = fma(x, y, -p);
-  p *= sign;
-  e *= sign;
-  const double s = hi + p;
-  const double bb = s - hi;
-  const double err = (hi - (s - bb)) + (p - bb);
-  hi = s;
-  lo += err + e;
 }
 
 // Diagonal walk.  grid (L, L, 4); thread t walks the diagonal q' - q = t of pair (l, l'): entries (k, t + k).
@@ -338,10 +366,16 @@ int stage_stats(Handle& h) {
     return OK;
   }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[0], h.st));
-  syrk_toeplitz_kernel<<<dim3(ntile, 4), 256, sm, h.st>>>(h.Sp, h.R, D, ntile, SEG, maxl, pmask);
+  int nl = 0;
+  for (int m0 = 0; m0 < D.M; m0 += 4) {
+    const int mc = std::min(4, D.M - m0);
+    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, pmask, m0, mc);
+    syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, pmask, mc, m0 == 0, m0 + 4 >= D.M);
+    nl += 2;
+  }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
   rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
-  h.launches += 3;
+  h.launches += 2 + nl;
   APV_CUDA_TRY(cudaGetLastError());
   return OK;
 }

@@ -1,0 +1,269 @@
+"""GPU: size-independent properties at BASELINE's full sizes (cfg-3: n = 4096) where the oracle would take
+minutes per block, the mu x V sweep (cfg-4 semantics), and ragged / degenerate shapes."""
+import numpy as np
+import pytest
+
+from tests._golden import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    from ap_vast_unofficial_b200 import apvast
+    return apvast
+
+
+@pytest.fixture(scope="module")
+def cfg3_run():
+    from ap_vast_unofficial_b200.workloads import make_workload
+    wl = make_workload("cfg3", n_blocks=4)
+    np.random.seed(0)
+    eng = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **wl["cfg"])
+    H = eng.hop_size
+    outs = []
+    for t in range(4):
+        outs.append(eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H]))
+    return wl, eng, outs
+
+
+def test_cfg3_statistics_rows_against_direct_sums(cfg3_run):
+    wl, eng, _ = cfg3_run
+    from oracle.apvast_oracle import toeplitz_rows
+    J, L, M = eng.filter_length, eng.number_of_srcs, eng.number_of_mics
+    S = eng.loudspeaker_weighted_response_B_to_A_buffer          # (N, L, M)
+    R = eng.R_B_to_A
+    assert np.array_equal(R, R.T)
+    rows = [0, J * 7 + 100, L * J - 1]
+    want = np.zeros((len(rows), L * J))
+    for m in range(M):
+        Y = np.concatenate([toeplitz_rows(S[:, l, m], J) for l in range(L)], axis=0)
+        want += Y[rows] @ Y.T
+    assert rel(R[rows], want) < 1e-12
+    # r_B against the direct sum
+    ST = eng.loudspeaker_weighted_target_response_B_to_B_buffer
+    SB = eng.loudspeaker_weighted_response_B_to_B_buffer
+    r = np.zeros(L * J)
+    for m in range(M):
+        Y = np.concatenate([toeplitz_rows(SB[:, l, m], J) for l in range(L)], axis=0)
+        r += Y @ ST[J:, m]
+    assert rel(eng.r_B[:, 0], r) < 1e-12
+
+
+def test_cfg3_joint_diagonalisation_identities(cfg3_run):
+    """jdiag.m:33-35 at n = 4096: U'(R_D + reg I)U = I, U'R_B U = Lambda, eigenvalues descending."""
+    wl, eng, _ = cfg3_run
+    n = eng.filter_length * eng.number_of_srcs
+    for RB, RD, U, lam in ((eng.R_A_to_A, eng.R_A_to_B, eng.U_A, eng.lambda_A),
+                           (eng.R_B_to_B, eng.R_B_to_A, eng.U_B, eng.lambda_B)):
+        assert np.all(np.diff(lam) <= 0)
+        G = U.T @ (RD @ U + 1e-7 * U)
+        assert np.max(np.abs(G - np.eye(U.shape[1]))) < 1e-8
+        A = U.T @ (RB @ U)
+        assert np.max(np.abs(A - np.diag(lam))) / lam[0] < 1e-8
+        # residual of the generalised eigenproblem R_B u = lambda (R_D + reg I) u
+        res = RB @ U - (RD @ U + 1e-7 * U) * lam[None, :]
+        assert np.linalg.norm(res) / (np.linalg.norm(RB) * np.linalg.norm(U)) < 1e-10
+
+
+def test_cfg3_filter_sum_and_first_block_rendering(cfg3_run):
+    wl, eng, outs = cfg3_run
+    V, J, L, Nb, H = eng.number_of_eigenvectors, eng.filter_length, eng.number_of_srcs, eng.block_size, eng.hop_size
+    U, lam, r = eng.U_A, eng.lambda_A, eng.r_A[:, 0]
+    a = (U.T @ r) / (lam + eng.mu)
+    want = np.cumsum(U * a[None, :], axis=1).T
+    assert rel(eng.w_A[:, :, 0], want) < 1e-12
+    # rendering of the LAST block against the reference formula needs the previous overlap tail: use linearity
+    # instead -- out[v] - out[v-1] is the rendering of the single component a_v u_v
+    oA = np.stack(outs[-1][0])
+    x = eng.input_A_block[:, 0]
+    win = np.sin(np.pi / Nb * np.arange(Nb))
+    X = np.fft.rfft(win * x)
+    for v in (1, V - 1):
+        comp = (eng.w_A[v, :, 0] - eng.w_A[v - 1, :, 0]).reshape(L, J).T
+        frame = win[:, None] * np.fft.irfft(X[:, None] * np.fft.rfft(comp, Nb, axis=0), Nb, axis=0)
+        # overlap buffers differ between ranks by the same component filtered in the previous block too; compare
+        # the parts of the current frame only through the overlap buffer difference
+        Gd = eng.output_A_overlap_buffer[v] - eng.output_A_overlap_buffer[v - 1]
+        assert rel(Gd[H:], frame[H:]) < 1e-9
+    assert oA.shape == (V, H, L)
+
+
+def test_cfg3_structured_statistics_equal_dmma(cfg3_run):
+    wl, eng, _ = cfg3_run
+    np.random.seed(0)
+    e2 = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, stats_mode=2, **wl["cfg"])
+    H = e2.hop_size
+    for t in range(4):
+        e2.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+    errs = {nm: rel(getattr(e2, nm), getattr(eng, nm)) for nm in ("R_A_to_A", "R_A_to_B", "R_B_to_A", "R_B_to_B")}
+    werr = max(rel(e2.w_A[v], eng.w_A[v]) for v in range(eng.number_of_eigenvectors))
+    print("structured vs DMMA at cfg-3:", errs, "max filter diff", werr)
+    assert max(errs.values()) < 1e-12, errs
+    assert werr < 1e-8, werr
+
+
+def test_mu_sweep_matches_oracle_rank_loop():
+    """BASELINE cfg-4 semantics: filters for several mu from ONE joint diagonalisation (the reference would redo
+    jdiag per mu, apvast.py:378-382), all ranks 1..V, against the oracle's rank loop per mu."""
+    from oracle.apvast_oracle import ApvastOracle
+    rng = np.random.default_rng(9)
+    K, L, M = 48, 4, 3
+    rA = 1e-3 * rng.standard_normal((K, L, M)); rB = 1e-3 * rng.standard_normal((K, L, M))
+    cfg = dict(block_size=128, filter_length=12, modeling_delay=3, reference_index_A=0, reference_index_B=1,
+               number_of_eigenvectors=48, mu=1.0, statistics_buffer_length=200, perceptual=False)   # V = n
+    np.random.seed(1); gpu = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    np.random.seed(1); ora = ApvastOracle(rir_A=rA, rir_B=rB, **cfg)
+    for t in range(6):
+        a, b = rng.standard_normal(64), rng.standard_normal(64)
+        gpu.process_input_buffers(a, b); ora.process_input_buffers(a, b)
+    mus = np.logspace(-3, 1, 8)
+    wA, wB = gpu.sweep(mus)
+    lam, U, r = ora.lambda_A, ora.U_A, ora.r_A[:, 0]
+    gap = np.abs(np.diff(lam)) / lam[0]
+    for k, mu in enumerate(mus):
+        want = np.cumsum(U * ((U.T @ r) / (lam + mu))[None, :], axis=1).T
+        for v in range(48):
+            if v == 47 or gap[v] > 1e-9:
+                assert rel(wA[k, v], want[v]) < 1e-8, (k, v)
+        n = 48
+        closed = np.linalg.solve(ora.R_A_to_A + mu * (ora.R_A_to_B + 1e-7 * np.eye(n)), r)
+        assert rel(wA[k, -1], closed) < 1e-8
+
+
+@pytest.mark.parametrize("shape", [dict(L=1, J=6, M=1, V=3), dict(L=3, J=1, M=2, V=2), dict(L=2, J=5, M=1, V=1),
+                                   dict(L=5, J=3, M=4, V=15)])
+def test_degenerate_shapes_against_oracle(shape):
+    from oracle.apvast_oracle import ApvastOracle
+    rng = np.random.default_rng(shape["L"] * 10 + shape["J"])
+    K, L, M, J, V = 9, shape["L"], shape["M"], shape["J"], shape["V"]
+    rA = 1e-3 * rng.standard_normal((K, L, M)); rB = 1e-3 * rng.standard_normal((K, L, M))
+    cfg = dict(block_size=32, filter_length=J, modeling_delay=0, reference_index_A=0, reference_index_B=L - 1,
+               number_of_eigenvectors=V, mu=0.5, statistics_buffer_length=40, perceptual=False)
+    np.random.seed(2); gpu = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    np.random.seed(2); ora = ApvastOracle(rir_A=rA, rir_B=rB, **cfg)
+    for t in range(5):
+        a, b = rng.standard_normal(16), rng.standard_normal(16)
+        og = gpu.process_input_buffers(a, b); oo = ora.process_input_buffers(a, b)
+        assert rel(gpu.R_A_to_A, ora.R_A_to_A) < 1e-12 and rel(gpu.r_B, ora.r_B) < 1e-12
+        lam = ora.lambda_A
+        gap = np.abs(np.diff(lam[:V + 1])) / lam[0] if V < L * J else np.r_[np.abs(np.diff(lam)) / lam[0], 1.0]
+        for v in range(V):
+            if gap[v] > 1e-9:
+                assert rel(gpu.w_A[v], ora.w_A[v]) < 1e-8, (t, v)
+        assert np.max(np.abs(np.array(og[2]) - np.array(oo[2]))) < 1e-12          # target stream (block 0 is exactly 0)
+
+
+def test_nan_input_raises_linalgerror_like_the_reference():
+    rng = np.random.default_rng(0)
+    r = 1e-3 * rng.standard_normal((8, 2, 2))
+    eng = _engine()(32, r, r, 4, 1, 0, 0, 2, 1.0, 24, perceptual=False)
+    x = rng.standard_normal(16)
+    eng.process_input_buffers(x, x)
+    bad = x.copy(); bad[3] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.process_input_buffers(bad, x)
+
+
+def test_perceptual_device_model_at_reference_block_size():
+    """perceptual=True at Nb = 2048 / fs = 48 kHz (44 auditory channels): on-device masking_gain against the NumPy
+    restatement of perceptualModel.m driving the oracle (the gain formula itself is parity-unpinned)."""
+    from oracle.apvast_oracle import ApvastOracle
+    rng = np.random.default_rng(44)
+    K, L, M = 128, 3, 2
+    dec = np.exp(-np.arange(K) / 30.0).reshape(-1, 1, 1)
+    rA = 1e-3 * rng.standard_normal((K, L, M)) * dec; rB = 1e-3 * rng.standard_normal((K, L, M)) * dec
+    cfg = dict(block_size=2048, filter_length=16, modeling_delay=4, reference_index_A=0, reference_index_B=2,
+               number_of_eigenvectors=8, mu=1.0, statistics_buffer_length=2048, perceptual=True)
+    np.random.seed(5); gpu = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    np.random.seed(5); ora = ApvastOracle(rir_A=rA, rir_B=rB, **cfg)
+    assert gpu.model.n_channels == 44
+    for t in range(5):
+        a, b = rng.standard_normal(1024), rng.standard_normal(1024)
+        og = gpu.process_input_buffers(a, b); oo = ora.process_input_buffers(a, b)
+        assert rel(gpu.weighting_spectra_A, ora.weighting_spectra_A) < 1e-11
+        assert rel(gpu.weighting_spectra_B, ora.weighting_spectra_B) < 1e-11
+        assert rel(gpu.R_A_to_B, ora.R_A_to_B) < 1e-11
+        for v in range(8):
+            assert rel(gpu.w_A[v], ora.w_A[v]) < 1e-8, (t, v)
+        assert rel(np.array(og[1]), np.array(oo[1])) < 1e-8
+
+
+def test_process_blocks_and_checkpoint_roundtrip(tmp_path):
+    """apv_process_blocks == a loop of apv_process_block; get_state/set_state resumes a stream bit-exactly."""
+    import ctypes as C
+    from ap_vast_unofficial_b200 import _capi as capi
+    rng = np.random.default_rng(3)
+    K, L, M = 40, 3, 2
+    rA = 1e-3 * rng.standard_normal((K, L, M)); rB = 1e-3 * rng.standard_normal((K, L, M))
+    cfg = dict(block_size=64, filter_length=8, modeling_delay=2, reference_index_A=1, reference_index_B=0,
+               number_of_eigenvectors=5, mu=1.0, statistics_buffer_length=96, perceptual=False)
+    sA, sB = rng.standard_normal(10 * 32), rng.standard_normal(10 * 32)
+    np.random.seed(0); e1 = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    np.random.seed(0); e2 = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    outs1 = [np.stack(e1.process_input_buffers(sA[t * 32:(t + 1) * 32], sB[t * 32:(t + 1) * 32])[0]) for t in range(10)]
+    V, H, Ls, n = 5, 32, 3, 24
+    oA = np.zeros((10, V, H, Ls)); oB = np.zeros((10, V, H, Ls)); w = np.zeros((10, 2, V, n))
+    capi.check(capi.lib().apv_process_blocks(e2._h, 10, capi.ptr(sA), capi.ptr(sB), capi.ptr(oA), capi.ptr(oB), None, None,
+                                             capi.ptr(w)))
+    for t in range(10):
+        assert np.array_equal(oA[t], outs1[t])
+    assert np.array_equal(w[9, 0], e1.w_A[:, :, 0])
+    # checkpoint after 6 blocks, resume in a fresh engine, blocks 6..9 must be identical
+    np.random.seed(0); e3 = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    for t in range(6):
+        e3.process_input_buffers(sA[t * 32:(t + 1) * 32], sB[t * 32:(t + 1) * 32])
+    path = str(tmp_path / "ckpt.npz")
+    e3.save_state(path)
+    np.random.seed(123); e4 = _engine()(rir_A=rA, rir_B=rB, **cfg)
+    e4.load_state(path)
+    for t in range(6, 10):
+        o = np.stack(e4.process_input_buffers(sA[t * 32:(t + 1) * 32], sB[t * 32:(t + 1) * 32])[0])
+        assert np.array_equal(o, outs1[t]), t
+
+
+@pytest.mark.parametrize("stats_mode", [0, 2])
+def test_cfg3_against_reference_golden(stats_mode):
+    """BASELINE cfg-3 (L=16, J=256, n=4096): 5 hops against what the UNMODIFIED reference produced on the same
+    synthetic workload (tests/golden/cfg3_reference.npz, oracle/make_golden_cfg3.py, ~1 min of CPU per hop)."""
+    import os
+    from ap_vast_unofficial_b200.workloads import make_workload
+    from tests._golden import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "cfg3_reference.npz"))
+    nblk = int(z["nblk"]); ranks = list(z["ranks"])
+    wl = make_workload("cfg3", n_blocks=nblk)
+    np.random.seed(int(z["seed"]))
+    eng = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, stats_mode=stats_mode, **wl["cfg"])
+    H, V = eng.hop_size, eng.number_of_eigenvectors
+    n = eng.filter_length * eng.number_of_srcs
+    worst = {}
+    fails = []
+    for t in range(nblk):
+        outs = eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+        for nm in ("R_A_to_A", "R_A_to_B", "R_B_to_A", "R_B_to_B"):
+            R = getattr(eng, nm)
+            e = max(rel(np.diag(R), z[f"{nm}_diag_{t}"]), rel(R[[0, n // 2 - 1, n - 1], :], z[f"{nm}_rows_{t}"]))
+            worst["R"] = max(worst.get("R", 0), e)
+            assert e < 1e-12, (t, nm, e)
+        for zn in ("A", "B"):
+            assert rel(getattr(eng, f"r_{zn}")[:, 0], z[f"r_{zn}_{t}"]) < 1e-12
+            lam_ref = z[f"lambda_{zn}_{t}"]
+            lam = getattr(eng, f"lambda_{zn}")
+            el = float(np.max(np.abs(lam - lam_ref[:V])) / lam_ref[0])
+            worst["lambda"] = max(worst.get("lambda", 0), el)
+            assert el < 1e-9, (t, zn, el)       # eps * cond(R_D + reg I): the pencil is ill-conditioned at this size
+            gap = np.abs(np.diff(lam_ref)) / lam_ref[0]          # V gaps (V+1 eigenvalues stored)
+            w = getattr(eng, f"w_{zn}")[:, :, 0]
+            for i, v in enumerate(ranks):
+                e = rel(w[v], z[f"w_{zn}_{t}"][i])
+                key = "w_resolved" if gap[v] > 1e-6 else "w_close_pair"
+                worst[key] = max(worst.get(key, 0), e)
+                # 1e-8 is the north-star bar; it is reachable only where the reference's own filter is well
+                # defined, i.e. the eigenvalue gap to the next rank is resolved
+                fails.append((t, zn, v, e, float(gap[v]))) if e >= (1e-8 if gap[v] > 1e-6 else 1e-5) else None
+        for i, zn in enumerate(("A", "B")):
+            got = np.stack([outs[i][v] for v in (0, V - 1)])
+            e = rel(got, z[f"out_{zn}_{t}"])
+            worst["out"] = max(worst.get("out", 0), e)
+            fails.append((t, "out_" + zn, e)) if e >= 1e-7 else None
+    print("cfg3 vs reference golden (stats_mode=%d): worst relative errors" % stats_mode, worst, "violations", fails)
+    assert not fails, fails
