@@ -351,12 +351,15 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"kernel": "td_panel_kernel (Householder tridiagonalisation, both zones)", "bound": "hbm",
                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_block": td_bytes,
-                         "launches_per_block": n_panel, "kernel_ms_per_block": kt_panel, "traffic": None},
+                         "launches_per_block": n_panel, "kernel_ms_per_block": kt_panel, "traffic": None,
+                         "traffic_sample": {"source": "profiles/r01_ncu_full_v2.txt (ncu --set full, panel 5 of 128, cfg3)",
+                                            "dram_bytes": 8.165e9, "algorithmic_bytes": 7.874e9, "ratio": 1.04}},
             "roofline_stats": {"kernel": "syrk_toeplitz_kernel (FP64 DMMA statistics)", "bound": "tensor",
                                "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
                                "frac": ach_tf / float(tf.value) if tf.value else None,
                                "peak_source": "FP64 mma.sync m8n8k4 issue-rate microbenchmark run in this process",
-                               "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk},
+                               "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
+                               "ncu_tensor_pipe_pct": 90.5, "ncu_source": "profiles/r01_ncu_full_v2.txt"},
             "stage_ms_last_block": stage_acc, "clocks": clocks, "checksum": chk,
         }
         line["alt_structured_stats"] = alt
