@@ -111,7 +111,8 @@ int check_info(Handle& h) {
       return fail(ENOTPD, "Matrix is not positive definite (zone %c, pivot %d)", h.zones[zi] == 0 ? 'A' : 'B',
                   info[zi * 4]);
     if (info[zi * 4 + 1] != 0)
-      return fail(ENOCONV, "inverse iteration did not converge (zone %c)", h.zones[zi] == 0 ? 'A' : 'B');
+      return fail(ENOCONV, "eigen-solver did not converge (zone %c, flags %d)", h.zones[zi] == 0 ? 'A' : 'B',
+                  info[zi * 4 + 1]);
   }
   return OK;
 }

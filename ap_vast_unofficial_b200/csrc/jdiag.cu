@@ -771,6 +771,94 @@ __global__ void __launch_bounds__(BTT) eig_backsolve_kernel(const double* __rest
   for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] = xs[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small-n path (eig_mode 2, automatic for n <= JACOBI_AUTO_N): one-sided (Hestenes) Jacobi on the symmetric C held
+// in shared memory, one CTA per zone, one warp per column pair, round-robin parallel ordering.  Columns of G = C V
+// are rotated until mutually orthogonal; V accumulates the rotations, so V holds the eigenvectors and
+// lambda_i = v_i . g_i (sign included, no division -- rank-deficient C is fine).  Full spectrum, no tridiagonal
+// stage, no clusters to repair; used where the matrix fits in one SM (2 n^2 doubles).
+constexpr int JACOBI_MAX_N = 112;
+constexpr int JACOBI_AUTO_N = 48;
+
+__global__ void __launch_bounds__(256) eig_jacobi_kernel(const double* __restrict__ Cm, double* __restrict__ lam,
+                                                         double* __restrict__ Zt, int* __restrict__ info, int n, int ldn,
+                                                         int V) {
+  extern __shared__ double jsm[];
+  const int np = (n + 1) & ~1;
+  double* G = jsm;                 // column-major np x np
+  double* Vm = jsm + (size_t)np * np;
+  __shared__ double lamv[JACOBI_MAX_N + 2];
+  __shared__ int rotated;
+  const int z = blockIdx.x;
+  const double* C = Cm + (size_t)z * n * ldn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int e = threadIdx.x; e < np * np; e += blockDim.x) {
+    const int c = e / np, r = e - c * np;
+    G[e] = (r < n && c < n) ? C[(size_t)r * ldn + c] : 0.0;
+    Vm[e] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int m1 = np - 1;
+  int sweep = 0;
+  for (; sweep < 40; ++sweep) {
+    if (threadIdx.x == 0) rotated = 0;
+    __syncthreads();
+    for (int rd = 0; rd < m1; ++rd) {
+      for (int k = warp; k < np / 2; k += nw) {
+        int p, q;
+        if (k == 0) { p = m1; q = rd; }
+        else { p = (rd + k) % m1; q = (rd - k + m1) % m1; }
+        double* gp = G + (size_t)p * np;
+        double* gq = G + (size_t)q * np;
+        double a = 0.0, b = 0.0, g = 0.0;
+        for (int i = lane; i < np; i += 32) {
+          const double x = gp[i], y = gq[i];
+          a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+        }
+        a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+        if (fabs(g) > DBL_EPSILON * sqrt(a * b) && g != 0.0) {        // warp-uniform
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          double* vp = Vm + (size_t)p * np;
+          double* vq = Vm + (size_t)q * np;
+          for (int i = lane; i < np; i += 32) {
+            const double x = gp[i], y = gq[i];
+            gp[i] = cs * x - sn * y;
+            gq[i] = sn * x + cs * y;
+            const double u = vp[i], w = vq[i];
+            vp[i] = cs * u - sn * w;
+            vq[i] = sn * u + cs * w;
+          }
+          if (lane == 0) rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (!rotated) break;
+    __syncthreads();
+  }
+  if (sweep >= 40 && threadIdx.x == 0) atomicOr(&info[z * 4 + 1], 2);
+  for (int c = warp; c < n; c += nw) {
+    double s = 0.0;
+    for (int i = lane; i < np; i += 32) s = fma(Vm[(size_t)c * np + i], G[(size_t)c * np + i], s);
+    s = warp_sum(s);
+    if (lane == 0) lamv[c] = s;
+  }
+  __syncthreads();
+  // rank sort, descending
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const double lc = lamv[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (lamv[j] > lc) || (lamv[j] == lc && j < c);
+    if (rank < V) {
+      lam[(size_t)z * V + rank] = lc;
+      double* out = Zt + ((size_t)z * V + rank) * n;
+      for (int i = 0; i < n; ++i) out[i] = Vm[(size_t)c * np + i];
+    }
+  }
+}
+
 template <typename Kern>
 int ensure_smem(Kern k, size_t bytes) {
   if (bytes > 48 * 1024) APV_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -953,6 +1041,22 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
 
   APV_CUDA_TRY(cudaEventRecord(ws.ev[2], st));
   // ---- blocked Householder tridiagonalisation of Cm
+  const bool use_jacobi = (ws.eig_mode == 2 && n <= JACOBI_MAX_N) || (ws.eig_mode == 0 && n <= JACOBI_AUTO_N);
+  if (use_jacobi) {
+    const int np = (n + 1) & ~1;
+    const size_t jsm = (size_t)2 * np * np * sizeof(double);
+    APV_TRY(ensure_smem(eig_jacobi_kernel, jsm));
+    eig_jacobi_kernel<<<nz, 256, jsm, st>>>(ws.Cm, ws.lam, ws.Zt, ws.info, n, ldn, V);
+    ++nl;
+    for (int e = 3; e <= 5; ++e) APV_CUDA_TRY(cudaEventRecord(ws.ev[e], st));
+    APV_TRY(ensure_smem(eig_backsolve_kernel, (size_t)n * sizeof(double)));
+    eig_backsolve_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.Lm, ws.Dinv, ws.Zt, n, ldn, V, nblk);
+    ++nl;
+    APV_CUDA_TRY(cudaEventRecord(ws.ev[6], st));
+    APV_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += nl;
+    return OK;
+  }
   APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));
   // ---- top-V eigenpairs of T

@@ -47,14 +47,15 @@ def _spd_pair(n, rng, cols=3):
     return (X * sc[:, None]) @ (X * sc[:, None]).T, Y @ Y.T
 
 
-@pytest.mark.parametrize("n,V", [(24, 24), (70, 10), (100, 100), (257, 33), (640, 64)])
-def test_jdiag_identities_and_filters(n, V):
+@pytest.mark.parametrize("n,V,eig_mode", [(24, 24, 1), (24, 24, 2), (70, 10, 1), (70, 10, 2), (100, 100, 1), (100, 100, 2),
+                                          (111, 7, 2), (257, 33, 0), (640, 64, 0)])
+def test_jdiag_identities_and_filters(n, V, eig_mode):
     """jdiag.m:33-35 identities and the filter sum against the reference route (oracle jdiag)."""
     from ap_vast_unofficial_b200 import jdiag
     from oracle.apvast_oracle import jdiag as jdiag_ref
     rng = np.random.default_rng(n + V)
     A, B = _spd_pair(n, rng)
-    U, D = jdiag(A, B, number_of_eigenvectors=V)
+    U, D = jdiag(A, B, number_of_eigenvectors=V, eig_mode=eig_mode)
     lam = np.diag(D)
     Ur, Dr = jdiag_ref(A, B)
     lr = np.diag(Dr)[:V]
@@ -81,14 +82,15 @@ def test_jdiag_not_positive_definite():
         jdiag(A, B, number_of_eigenvectors=4)
 
 
-def test_jdiag_rank_deficient_bright():
+@pytest.mark.parametrize("eig_mode", [1, 2])
+def test_jdiag_rank_deficient_bright(eig_mode):
     """Degenerate zero eigenvalues (bright matrix of rank 5): the rank-n filter is still the closed form."""
     from ap_vast_unofficial_b200 import jdiag
     n = 48
     rng = np.random.default_rng(5)
     X = rng.standard_normal((n, 5)); A = X @ X.T
     Y = rng.standard_normal((n, 2 * n)); B = Y @ Y.T
-    U, D = jdiag(A, B)
+    U, D = jdiag(A, B, eig_mode=eig_mode)
     lam = np.diag(D)
     r = rng.standard_normal(n)
     w = U @ ((U.T @ r) / (lam + 0.5))

@@ -27,9 +27,12 @@ def _check(res, name, wtol=1e-8):
             assert v <= tol, (name, t, k, v)
 
 
+@pytest.mark.parametrize("eig_mode", [1, 2])
 @pytest.mark.parametrize("name", ["tiny", "tiny_hop", "tiny_runA", "mid"])
-def test_golden_small(name):
-    eng, g, res = replay(_engine(), name)
+def test_golden_small(name, eig_mode):
+    """eig_mode 1 = tridiagonalisation + bisection + inverse iteration, 2 = shared-memory Jacobi (n <= 112; "mid" with
+    n = 128 falls back to the tridiagonal path)."""
+    eng, g, res = replay(_engine(), name, extra_ctor=dict(eig_mode=eig_mode))
     _check(res, name)
     for a, v in compare_state(eng, g).items():
         tol = 1e-8 if a.startswith("output_") else 1e-12
@@ -49,13 +52,14 @@ def test_golden_structured_statistics(name):
     _check(res, name + "-structured")
 
 
-def test_golden_full_rank_closed_form():
+@pytest.mark.parametrize("eig_mode", [1, 2])
+def test_golden_full_rank_closed_form(eig_mode):
     """V = n: per-rank filters inside a degenerate eigenvalue cluster are basis-dependent (sign/rotation
     ambiguity, as for eigenvectors), so ranks are compared only where the eigenvalue gap is resolved; the
     last rank must equal the closed form w = (R_B + mu (R_D + reg I))^-1 r_B (apVast.m:115-118, vast.m:92)."""
     g, cfg, ctor = load_case("tiny_full")
     np.random.seed(int(g["seed"]))
-    eng = _engine()(rir_A=g["rir_A"], rir_B=g["rir_B"], **cfg, **ctor)
+    eng = _engine()(rir_A=g["rir_A"], rir_B=g["rir_B"], eig_mode=eig_mode, **cfg, **ctor)
     for t in range(int(g["nblk"])):
         eng.process_input_buffers(g["input_A"][t], g["input_B"][t])
         for z in ("A", "B"):
