@@ -12,6 +12,8 @@ CONFIGS = {
     "cfg2": dict(L=8, M=8, J=128, K=1024, Nb=2048, N=2048, V=64, d=32, seconds=10.0),
     "cfg3": dict(L=16, M=16, J=256, K=1024, Nb=2048, N=2048, V=64, d=32, seconds=60.0),
     "small": dict(L=4, M=4, J=32, K=128, Nb=256, N=384, V=16, d=8, seconds=0.2),
+    # BASELINE configs[4] array size (L=32, J=256, n=8192) as a 2-zone problem (the reference has no 4-zone form)
+    "cfg5_2zone": dict(L=32, M=16, J=256, K=1024, Nb=2048, N=2048, V=64, d=32, seconds=1.0),
 }
 
 

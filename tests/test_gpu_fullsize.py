@@ -267,3 +267,34 @@ def test_cfg3_against_reference_golden(stats_mode):
             fails.append((t, "out_" + zn, e)) if e >= 1e-7 else None
     print("cfg3 vs reference golden (stats_mode=%d): worst relative errors" % stats_mode, worst, "violations", fails)
     assert not fails, fails
+
+
+def test_largest_array_size_n8192_identities():
+    """BASELINE configs[4] array size (L=32, J=256, n=8192), run as a 2-zone problem: statistics rows against direct
+    sums and the joint-diagonalisation identities at the maximum size the tables are built for."""
+    from ap_vast_unofficial_b200.workloads import make_workload
+    from oracle.apvast_oracle import toeplitz_rows
+    wl = make_workload("cfg5_2zone", n_blocks=3)
+    np.random.seed(0)
+    eng = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, run_B=False, **wl["cfg"])
+    H = eng.hop_size
+    for t in range(3):
+        eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+    J, L, M = eng.filter_length, eng.number_of_srcs, eng.number_of_mics
+    n = J * L
+    assert n == 8192
+    S = eng.loudspeaker_weighted_response_A_to_B_buffer
+    RD = eng.R_A_to_B
+    rows = [1, n - 2]
+    want = np.zeros((2, n))
+    for m in range(M):
+        Y = np.concatenate([toeplitz_rows(S[:, l, m], J) for l in range(L)], axis=0)
+        want += Y[rows] @ Y.T
+    assert rel(RD[rows], want) < 1e-12
+    U, lam, RB = eng.U_A, eng.lambda_A, eng.R_A_to_A
+    assert np.all(np.diff(lam) <= 0)
+    G = U.T @ (RD @ U + 1e-7 * U)
+    assert np.max(np.abs(G - np.eye(U.shape[1]))) < 1e-8
+    res = RB @ U - (RD @ U + 1e-7 * U) * lam[None, :]
+    assert np.linalg.norm(res) / (np.linalg.norm(RB) * np.linalg.norm(U)) < 1e-10
+    print("n=8192 stage times:", {k: round(v, 1) for k, v in eng.stage_times().items()})
