@@ -7,16 +7,19 @@
 // the trailing update A22 -= V W^T + W V^T is one DMMA GEMM  A22 -= Z1 Z2^T  with K = 2 NBT (issued by
 // the host between panel kernels).
 //
-// ONE persistent cooperative kernel per panel of NBT columns, two grid barriers per column:
+// ONE persistent cooperative kernel per panel of NBT columns, two barriers per column (per zone: the CTAs of a
+// zone synchronise among themselves through a monotone arrival counter, so the zones may drift apart):
 //
 //   phase P1(j): (jj > 0) raw w of the previous column,  w = tau (y - V (W^T v) - W (V^T v)),  its
 //                partial w.v, and the updated column j as a function of the still unknown
 //                gamma = tau/2 (w.v):   x = a + 2 gamma v_prev   (a goes to colbuf)
-//   --- grid barrier ---
+//   --- zone barrier ---
 //   phase P2(j): gamma, x and the reflector scalars (beta, tau, s = 1/(alpha-beta)) -- every CTA
 //                redundantly, it needs all of x for its GEMV rows anyway --, final W column of the
 //                previous reflector, y = A[j+1:, j+1:] v for the CTA's rows (the HBM/L2-bound part:
-//                4 x 16-byte loads in flight per lane, 16 warps per SM), partial (panel)^T v.
+//                two rows per warp trip, 16 x 16-byte loads in flight per lane, 16 warps per SM -- with 4 in
+//                flight the product was limited by per-SM memory-level parallelism, not by HBM),
+//                partial (panel)^T v.
 //                v = s x + c e_{j+1} (c = 1 - s alpha) is not materialised for the product:
 //                A v = s (A x) + c A[:, j+1], so no rescaling pass sits in front of the big read.
 //   --- grid barrier ---
@@ -49,11 +52,28 @@ struct TdPanel {
   double* vcur;   // [nz][2][n]        current reflector, double buffered by column parity
   double* pwv;    // [nz][GMAX]        partial w.v
   double* tpart;  // [nz][GMAX][2 NBT] partial (panel col)^T v
+  unsigned long long* bar;   // [nz] monotone arrival counters of the per-zone barriers
   int n, ldn, nz;
   long long* dbg;
 };
 
 #define TD_TICK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { long long _t = clock64(); a.dbg[k] += _t - tk; tk = _t; } } while (0)
+
+// Barrier among the G CTAs of ONE zone problem (all CTAs are co-resident: cooperative launch).  The two zones
+// synchronise independently, so one zone's latency-bound phases overlap the other zone's HBM-bound product instead
+// of both zones idling together.  Monotone 64-bit arrival counter: barrier k completes when it reaches (k+1) G.
+__device__ __forceinline__ void zone_sync(unsigned long long* bar, int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(bar, 1ull);
+    const unsigned long long target = (old / (unsigned long long)G + 1ull) * (unsigned long long)G;
+    while (*reinterpret_cast<volatile unsigned long long*>(bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ void chunk_of(int lo, int hi, int G, int g, int& a, int& b) {
   const int rows = hi - lo, per = (rows + G - 1) / G;
@@ -246,32 +266,42 @@ __device__ __forceinline__ void td_phase2(const TdPanel& a, double* xs, double* 
   const int c0 = (j + 1) & ~1;
   const int rs = max(r0, j + 1);
   const double* rowj1 = Cm + (size_t)(j + 1) * ldn;      // A[i][j+1] = A[j+1][i]
-  for (int i = rs + warp; i < r1; i += TDW) {
-    const double* row = Cm + (size_t)i * ldn;
-    const double aj1 = rowj1[i];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // two rows per warp trip, 8 independent 16-byte loads per row and lane (16 in flight per lane)
+  for (int i = rs + 2 * warp; i < r1; i += 2 * TDW) {
+    const bool two = i + 1 < r1;
+    const double* row0 = Cm + (size_t)i * ldn;
+    const double* row1 = Cm + (size_t)(two ? i + 1 : i) * ldn;
+    const double aj0 = rowj1[i], aj1 = two ? rowj1[i + 1] : 0.0;
+    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
     int k = c0 + 2 * lane;
-    for (; k + 192 < ldn; k += 256) {
-      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
-      const double2 a1 = __ldg(reinterpret_cast<const double2*>(row + k + 64));
-      const double2 a2 = __ldg(reinterpret_cast<const double2*>(row + k + 128));
-      const double2 a3 = __ldg(reinterpret_cast<const double2*>(row + k + 192));
-      const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
-      const double2 x1 = *reinterpret_cast<const double2*>(xs + k + 64);
-      const double2 x2 = *reinterpret_cast<const double2*>(xs + k + 128);
-      const double2 x3 = *reinterpret_cast<const double2*>(xs + k + 192);
-      s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
-      s1 = fma(a1.x, x1.x, s1); s1 = fma(a1.y, x1.y, s1);
-      s2 = fma(a2.x, x2.x, s2); s2 = fma(a2.y, x2.y, s2);
-      s3 = fma(a3.x, x3.x, s3); s3 = fma(a3.y, x3.y, s3);
+    for (; k + 448 < ldn; k += 512) {
+      double2 av[8], bv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) av[u] = __ldg(reinterpret_cast<const double2*>(row0 + k + 64 * u));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bv[u] = __ldg(reinterpret_cast<const double2*>(row1 + k + 64 * u));
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        const double2 x0 = *reinterpret_cast<const double2*>(xs + k + 64 * u);
+        const double2 x1 = *reinterpret_cast<const double2*>(xs + k + 64 * (u + 1));
+        s0 = fma(av[u].x, x0.x, s0); s0 = fma(av[u].y, x0.y, s0);
+        s1 = fma(av[u + 1].x, x1.x, s1); s1 = fma(av[u + 1].y, x1.y, s1);
+        t0 = fma(bv[u].x, x0.x, t0); t0 = fma(bv[u].y, x0.y, t0);
+        t1 = fma(bv[u + 1].x, x1.x, t1); t1 = fma(bv[u + 1].y, x1.y, t1);
+      }
     }
     for (; k < ldn; k += 64) {
-      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row + k));
+      const double2 a0 = __ldg(reinterpret_cast<const double2*>(row0 + k));
+      const double2 b0 = __ldg(reinterpret_cast<const double2*>(row1 + k));
       const double2 x0 = *reinterpret_cast<const double2*>(xs + k);
       s0 = fma(a0.x, x0.x, s0); s0 = fma(a0.y, x0.y, s0);
+      t0 = fma(b0.x, x0.x, t0); t0 = fma(b0.y, x0.y, t0);
     }
-    const double ax = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) ybuf[i] = fma(s, ax, c * aj1);
+    const double ax0 = warp_sum(s0 + s1), ax1 = warp_sum(t0 + t1);
+    if (lane == 0) {
+      ybuf[i] = fma(s, ax0, c * aj0);
+      if (two) ybuf[i + 1] = fma(s, ax1, c * aj1);
+    }
   }
   TD_TICK(5);
   __syncthreads();        // the CTA's Z1 writes above are visible to its own threads
@@ -314,7 +344,6 @@ __device__ __forceinline__ void td_phase3(const TdPanel& a, double* ex, int z, i
 }
 
 __global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdPanel a, int k0, int pw) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double td_sm[];
   double* xs = td_sm;                 // [ldn]
   double* ex = td_sm + a.ldn;         // scratch
@@ -326,17 +355,17 @@ __global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdPanel a, int k0, int
     const int j = k0 + jj;
     td_phase1(a, ex, z, g, G, j, jj, false);
     TD_TICK(0);
-    grid.sync();
+    zone_sync(a.bar + z, G);
     TD_TICK(1);
     td_phase2(a, xs, ex, z, g, G, j, jj, tk);
     TD_TICK(2);
-    grid.sync();
+    zone_sync(a.bar + z, G);
     TD_TICK(3);
   }
   const int r = k0 + pw;
   if (r < a.n) {
     td_phase1(a, ex, z, g, G, r, pw, true);
-    grid.sync();
+    zone_sync(a.bar + z, G);
     td_phase3(a, ex, z, g, G, r, pw);
   }
 }
@@ -344,7 +373,7 @@ __global__ void __launch_bounds__(TDT, 1) td_panel_kernel(TdPanel a, int k0, int
 }  // namespace
 
 size_t tridiag_scratch_doubles(int n, int nz) {
-  return (size_t)nz * GMAX * (2 * NBT + 1) + (size_t)nz * 2 * n;
+  return (size_t)nz * GMAX * (2 * NBT + 1) + (size_t)nz * 2 * n + 8;
 }
 
 int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches) {
@@ -369,6 +398,7 @@ int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   tp.pwv = ws.tdws;
   tp.tpart = tp.pwv + (size_t)nz * GMAX;
   tp.vcur = tp.tpart + (size_t)nz * GMAX * 2 * NBT;
+  tp.bar = reinterpret_cast<unsigned long long*>(tp.vcur + (size_t)nz * 2 * n);   // zeroed at allocation, stays a multiple of G
   tp.n = n; tp.ldn = ldn; tp.nz = nz;
   static long long* dbg = nullptr;
   if (getenv("APV_TD_DEBUG") && !dbg) cudaMalloc((void**)&dbg, 16 * sizeof(long long));
