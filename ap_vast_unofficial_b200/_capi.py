@@ -52,6 +52,7 @@ SIGNATURES = {
     "apv_set_mu": (C.c_int, [C.c_void_p, C.c_double]),
     "apv_set_gain_table": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, C.c_double]),
     "apv_sweep": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "apv_eval_zone": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
     "apv_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "apv_synchronize": (C.c_int, [C.c_void_p]),
     "apv_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -216,6 +216,18 @@ class apvast:
         capi.check(capi.lib().apv_sweep(self._h, mus.size, capi.ptr(mus), capi.ptr(out)))
         return (out[:, 0] if self.run_A else None), (out[:, 1] if self.run_B else None)
 
+    def evaluate(self, feeds, signal, zone="A"):
+        """Acoustic contrast and normalised signal distortion of loudspeaker feeds (T, L) at the control microphones,
+        on the device (``predictPressure.m:12-17``, ``main.m:120-130``).  Returns (AC dB, NMSE, NSD dB)."""
+        f = np.ascontiguousarray(feeds, dtype=np.float64)
+        s = np.ascontiguousarray(signal, dtype=np.float64).reshape(-1)[:f.shape[0]]
+        if f.ndim != 2 or f.shape[1] != self.number_of_srcs or s.size != f.shape[0]:
+            raise RuntimeError("feeds must be (T, number_of_srcs) and signal at least T long")
+        out = np.zeros(3)
+        capi.check(capi.lib().apv_eval_zone(self._h, 0 if zone in ("A", 0) else 1, f.shape[0], capi.ptr(f), capi.ptr(s),
+                                            capi.ptr(out)))
+        return float(out[0]), float(out[1]), float(out[2])
+
     def stage_times(self):
         """Device milliseconds of the last block: dict S1, S2S3, S4, S5, S6, S7, total; and launch count."""
         ms = (C.c_float * 7)()

@@ -462,6 +462,11 @@ int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out) {
   return rc;
 }
 
+int apv_eval_zone(apv_handle* h, int zone, int n_samples, const double* feeds, const double* signal, double* out3) {
+  if (!h || !feeds || !signal || !out3) return fail(EINVAL_, "null argument");
+  return eval_zone(*h, zone, n_samples, feeds, signal, out3);
+}
+
 int apv_device_ptr(apv_handle* h, int id, void** ptr) {
   if (!h || !ptr) return fail(EINVAL_, "null argument");
   TensorInfo ti = tensor_info(*h, id);

@@ -115,6 +115,7 @@ int stage_weighted(Handle& h);                                                //
 int stage_stats(Handle& h);                                                   // S4 (stats.cu)
 int stage_sweep(Handle& h, double mu, double* W_out);                         // S6 (render.cu)
 int stage_render(Handle& h);                                                  // a2 + S7
+int eval_zone(Handle& h, int zone, int T, const double* feeds, const double* signal, double* out3);  // metrics.cu
 int fft_plan(int n, int* rad, int* nrad);
 int fft_util(int n, int inverse, const double* in_ri, double* out_ri);        // test hook
 

@@ -132,6 +132,12 @@ int apv_set_gain_table(apv_handle* h, int n_channels, const double* G2, double C
  * w_out: (n_mu, 2, V, n) host buffer. */
 int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out);
 
+/* Evaluation of rendered loudspeaker feeds (callers' side of the path: Matlab/ControlMethods/predictPressure.m:12-17,
+ * Matlab/main.m:120-130).  feeds: (n_samples, L) host, signal: (n_samples) programme signal of the zone.
+ * out3: [0] acoustic contrast at the control microphones [dB], [1] NMSE between target and bright-zone pressure
+ * (mean over microphones), [2] 10 log10(NMSE) = normalised signal distortion [dB]. */
+int apv_eval_zone(apv_handle* h, int zone, int n_samples, const double* feeds, const double* signal, double* out3);
+
 /* Device pointer of a tensor (for torch.distributed / NCCL plumbing on the caller's side). */
 int apv_device_ptr(apv_handle* h, int tensor_id, void** ptr);
 int apv_synchronize(apv_handle* h);

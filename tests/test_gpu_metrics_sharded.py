@@ -40,6 +40,24 @@ def test_contrast_and_distortion_within_001_db():
             assert abs(nsd_g - nsd_o) < 0.01, (v, z, nsd_g, nsd_o)
 
 
+def test_device_metrics_match_host_definitions():
+    """apv_eval_zone (pressure + energies on the device) against the NumPy definitions of metrics.py."""
+    from ap_vast_unofficial_b200 import apvast
+    from ap_vast_unofficial_b200.metrics import evaluate_zone
+    rA, rB, cfg, sA, sB, nblk = _case()
+    np.random.seed(0)
+    eng = apvast(rir_A=rA, rir_B=rB, **cfg)
+    oa, ob = [], []
+    for t in range(nblk):
+        A, B, _, _ = eng.process_input_buffers(sA[t * 64:(t + 1) * 64], sB[t * 64:(t + 1) * 64])
+        oa.append(A[-1]); ob.append(B[-1])
+    fa, fb = np.concatenate(oa, axis=0), np.concatenate(ob, axis=0)
+    for zone, f, rb, rd, sig, ref in (("A", fa, rA, rB, sA, 1), ("B", fb, rB, rA, sB, 2)):
+        ac_h, nsd_h = evaluate_zone(f, rb, rd, sig, ref, 4)
+        ac_d, nmse_d, nsd_d = eng.evaluate(f, sig, zone)
+        assert abs(ac_d - ac_h) < 1e-9 and abs(nsd_d - nsd_h) < 1e-9, (zone, ac_d, ac_h, nsd_d, nsd_h)
+
+
 class _FakeDist:
     """Two ranks run one after the other on one GPU; point-to-point messages go through a dict."""
     box = {}
