@@ -30,6 +30,8 @@ class Config(C.Structure):
         ("perceptual", C.c_int32), ("normalize_gains", C.c_int32), ("eig_mode", C.c_int32),
         ("stats_mode", C.c_int32), ("device", C.c_int32),
         ("mu", C.c_double), ("reg", C.c_double), ("sampling_rate", C.c_double),
+        ("toeplitz_clean", C.c_int32), ("normalize_stats", C.c_int32), ("loading_mode", C.c_int32),
+        ("target_ref_per_zone", C.c_int32), ("bright_load", C.c_double), ("dark_load", C.c_double),
     ]
 
 

@@ -67,8 +67,12 @@ class apvast:
                  reference_index_A: int, reference_index_B: int, number_of_eigenvectors: int, mu: float,
                  statistics_buffer_length: int, hop_size: int = None, sampling_rate: int = 48000,
                  run_A: bool = True, run_B: bool = True, perceptual: bool = True, *, model=None,
-                 device: int = None, eig_mode: int = 0, stats_mode: int = 0):
+                 device: int = None, eig_mode: int = 0, stats_mode: int = 0, flavour: str = "python",
+                 fullscale_db: float = 94.0):
         self._h = None
+        if flavour not in ("python", "matlab"):
+            raise RuntimeError("flavour must be 'python' or 'matlab'")
+        self.flavour = flavour
         self.block_size = int(block_size)
         self.rir_A = rir_A
         self.rir_B = rir_B
@@ -76,6 +80,14 @@ class apvast:
         self.modeling_delay = int(modeling_delay)
         self.reference_index_A = int(reference_index_A)
         self.reference_index_B = int(reference_index_B)
+        # the MATLAB class takes an ascending LIST of ranks and returns one solution per element (apVast.m:204,527-544);
+        # the Python class takes an int V and returns ranks 1..V.  Both are accepted.
+        self._ranks = None
+        if np.ndim(number_of_eigenvectors) > 0:
+            self._ranks = [int(r) for r in np.ravel(number_of_eigenvectors)]
+            if self._ranks != sorted(self._ranks) or self._ranks[0] < 1:
+                raise RuntimeError("the list of ranks must be ascending and >= 1")
+            number_of_eigenvectors = self._ranks[-1]
         self.number_of_eigenvectors = int(number_of_eigenvectors)
         self._mu = float(mu)
         self.sampling_rate = sampling_rate
@@ -107,7 +119,7 @@ class apvast:
         if self.perceptual:
             if model is None:
                 from .perceptual import MaskingModel
-                self.model = MaskingModel(Nb, sampling_rate)
+                self.model = MaskingModel(Nb, sampling_rate, fullscale_db)
                 mode = 1
             else:
                 self.model = model
@@ -115,17 +127,23 @@ class apvast:
             np.seterr(divide="ignore")       # as the reference does (:76)
 
         # the six randn start buffers, drawn from the global NumPy RNG in the reference order (:124-129)
-        init = np.concatenate([(1e-3 * np.random.randn(Nb, L, M)).ravel() for _ in range(4)] +
-                              [(1e-3 * np.random.randn(Nb, M)).ravel() for _ in range(2)])
+        # (the MATLAB class starts from zeros, apVast.m:175-180, and does not touch the RNG)
+        init = None
+        if flavour == "python":
+            init = np.concatenate([(1e-3 * np.random.randn(Nb, L, M)).ravel() for _ in range(4)] +
+                                  [(1e-3 * np.random.randn(Nb, M)).ravel() for _ in range(2)])
+        matlab = flavour == "matlab"
 
         cfg = capi.Config(
             block_size=Nb, hop_size=self.hop_size, rir_length=K, n_srcs=L, n_mics=M,
             filter_length=self.filter_length, stats_length=self.statistics_buffer_length,
             n_eig=self.number_of_eigenvectors, modeling_delay=self.modeling_delay,
             ref_A=self.reference_index_A, ref_B=self.reference_index_B, run_A=int(self.run_A), run_B=int(self.run_B),
-            perceptual=mode, normalize_gains=int(bool(EXPERIMENTAL_NORMALIZE_GAINS)), eig_mode=int(eig_mode),
+            perceptual=mode, normalize_gains=2 if matlab else int(bool(EXPERIMENTAL_NORMALIZE_GAINS)),
+            eig_mode=int(eig_mode),
             stats_mode=int(stats_mode), device=-1 if device is None else int(device), mu=self._mu, reg=1e-7,
-            sampling_rate=float(sampling_rate))
+            sampling_rate=float(sampling_rate), toeplitz_clean=int(matlab), normalize_stats=int(matlab),
+            loading_mode=int(matlab), target_ref_per_zone=int(matlab), bright_load=1e-8, dark_load=5e-3)
         h = C.c_void_p()
         capi.check(capi.lib().apv_create(C.byref(cfg), capi.ptr(rA), capi.ptr(rB), capi.ptr(init), C.byref(h)))
         self._h = h
@@ -179,10 +197,11 @@ class apvast:
             capi.check(lib.apv_process_block(self._h, capi.ptr(a), capi.ptr(b), capi.ptr(oA), capi.ptr(oB),
                                              capi.ptr(oAt), capi.ptr(oBt)))
         self._blocks += 1
-        out_A = [oA[v] for v in range(V)] if self.run_A else None
-        out_B = [oB[v] for v in range(V)] if self.run_B else None
+        sel = range(V) if self._ranks is None else [r - 1 for r in self._ranks]
+        out_A = [oA[v] for v in sel] if self.run_A else None
+        out_B = [oB[v] for v in sel] if self.run_B else None
         # the reference returns V identical target arrays (:418,422,467-475,501,504)
-        return out_A, out_B, [oAt for _ in range(V)], [oBt for _ in range(V)]
+        return out_A, out_B, [oAt for _ in sel], [oBt for _ in sel]
 
     def _host_gains(self):
         """perceptual with a host model: W[:, m] = model.gain(time block), unit-norm (:313-324)."""
@@ -192,7 +211,9 @@ class apvast:
         for z in range(2):
             for m in range(M):
                 g = np.real(np.asarray(self.model.gain(frames[z, m]), dtype=complex))
-                if EXPERIMENTAL_NORMALIZE_GAINS:
+                if self.flavour == "matlab":
+                    g = g / np.sqrt(np.sum(g * g) + np.sum(g[1:-1] ** 2))
+                elif EXPERIMENTAL_NORMALIZE_GAINS:
                     g = g / np.linalg.norm(g)
                 W[z, m] = g
         self._set(capi.T_WEIGHT, W)
@@ -252,6 +273,9 @@ class apvast:
         a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
         capi.check(capi.lib().apv_set(self._h, tid, capi.ptr(a), a.size))
 
+    def _sel(self, w):
+        return w.copy() if self._ranks is None else w[[r - 1 for r in self._ranks]].copy()
+
     def _zone(self, z, on):
         if not on or self._blocks == 0:
             return None
@@ -263,14 +287,14 @@ class apvast:
         if not self.run_A:
             return None
         V, n = self.number_of_eigenvectors, self._n
-        return self._get(capi.T_W).reshape(2, V, n)[0].reshape(V, n, 1).copy()
+        return self._sel(self._get(capi.T_W).reshape(2, V, n)[0].reshape(V, n, 1))
 
     @property
     def w_B(self):
         if not self.run_B:
             return None
         V, n = self.number_of_eigenvectors, self._n
-        return self._get(capi.T_W).reshape(2, V, n)[1].reshape(V, n, 1).copy()
+        return self._sel(self._get(capi.T_W).reshape(2, V, n)[1].reshape(V, n, 1))
 
     @property
     def lambda_A(self):
@@ -372,7 +396,8 @@ class apvast:
             z = 0 if name == "output_A_t_overlap_buffer" else 1
             g = self._get(capi.T_OUT_OLA_T).reshape(2, Nb)[z]
             out = np.zeros((V, Nb, L))
-            lt = (self.filter_length * self.reference_index_A + self.modeling_delay) // self.filter_length
+            ref = self.reference_index_B if (z == 1 and self.flavour == "matlab") else self.reference_index_A
+            lt = (self.filter_length * ref + self.modeling_delay) // self.filter_length
             out[:, :, lt] = g[None, :]
             return out
         if name in ("input_A_block", "input_B_block"):

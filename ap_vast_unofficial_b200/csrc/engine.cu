@@ -98,7 +98,7 @@ int run_jdiag(Handle& h) {
     dark[zi] = h.R + (zone == 0 ? 1 : 2) * ms;
   }
   if (h.nz == 1) { bright[1] = bright[0]; dark[1] = dark[0]; }
-  return jdiag_run(h.jd, bright, dark, D.ldn, h.cfg.reg, h.st, &h.launches);
+  return jdiag_run(h.jd, bright, dark, D.ldn, h.cfg.loading_mode == 1 ? 0.0 : h.cfg.reg, h.st, &h.launches);
 }
 
 int check_info(Handle& h) {
@@ -129,6 +129,7 @@ int run_block(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1,
   APV_CUDA_TRY(cudaEventRecord(ev[2], h.st));
   if (!state_only) {
     APV_TRY(stage_stats(h));
+    if (h.cfg.loading_mode == 1) APV_TRY(stage_loading(h));
     APV_CUDA_TRY(cudaEventRecord(ev[3], h.st));
     APV_TRY(run_jdiag(h));
     APV_TRY(publish_eig(h));
@@ -165,10 +166,11 @@ int copy_out(Handle& h, double* out_A, double* out_B, double* out_A_t, double* o
     APV_CUDA_TRY(cudaMemcpyAsync(t.data(), h.d_out_t, 2 * (size_t)D.H * sizeof(double), cudaMemcpyDeviceToHost, h.st));
   }
   APV_CUDA_TRY(cudaStreamSynchronize(h.st));
-  const int lt = (D.J * D.refA + D.d) / D.J;
   for (int X = 0; X < 2; ++X) {
     double* o = X == 0 ? out_A_t : out_B_t;
     if (!o) continue;
+    const int ref = (X == 1 && h.cfg.target_ref_per_zone) ? D.refB : D.refA;   // Python uses index A for both (:418,422)
+    const int lt = (D.J * ref + D.d) / D.J;
     memset(o, 0, (size_t)D.H * D.L * sizeof(double));
     for (int i = 0; i < D.H; ++i) o[(size_t)i * D.L + lt] = t[(size_t)X * D.H + i];
   }
@@ -201,7 +203,8 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   D.F = D.Nb / 2 + 1;
   D.n = D.L * D.J;
   D.ldn = round_up(D.n, 8);
-  D.P = D.N - D.J;
+  D.clean = cfg->toeplitz_clean != 0;
+  D.P = D.N - D.J + (D.clean ? 1 : 0);
   if (D.K < 1 || D.L < 1 || D.M < 1 || D.J < 1 || D.V < 1) return fail(EINVAL_, "non-positive dimension");
   if (D.H > D.Nb) return fail(EINVAL_, "hop size larger than block size");
   if (D.H > D.N) return fail(EINVAL_, "hop size larger than statistics buffer");
@@ -217,6 +220,8 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   h->cfg = *cfg;
   h->cfg.hop_size = D.H;
   if (h->cfg.reg <= 0) h->cfg.reg = 1e-7;
+  if (h->cfg.bright_load <= 0) h->cfg.bright_load = 1e-8;
+  if (h->cfg.dark_load <= 0) h->cfg.dark_load = 5e-3;
   h->D = D;
   auto bail = [&](int code) { apv_destroy(h); return code; };
   if (cfg->device >= 0) {
@@ -248,6 +253,8 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->Wg, 2 * M * (size_t)D.F));
   TRYB(dalloc(&h->seed, 4 * L * L * (size_t)D.J));
   if (cfg->stats_mode != 2) TRYB(dalloc(&h->Pbuf, 16 * n * (size_t)D.ldn));
+  TRYB(dalloc(&h->norms, 64));
+  TRYB(dalloc(&h->pvec, 8 * n));
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
   TRYB(dalloc(&h->G, 2 * V * L * Nb));
   TRYB(dalloc(&h->Gt, 2 * Nb));
@@ -320,7 +327,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
 void apv_destroy(apv_handle* h) {
   if (!h) return;
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
-                h->Wg, h->seed, h->Pbuf, h->tframe, h->tspec, h->G, h->Gt, h->R, h->rvec, h->lam, h->U, h->W, h->d_in, h->d_out,
+                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->R, h->rvec, h->lam, h->U, h->W, h->d_in, h->d_out,
                 h->d_out_t};
   for (void* p : ps)
     if (p) cudaFree(p);

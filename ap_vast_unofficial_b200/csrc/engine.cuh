@@ -11,6 +11,7 @@ constexpr int STATS_KC = 64;   // K chunk of the statistics SYRK; fixes the padd
 // N statistics length, V ranks, n = L*J, P = N-J columns of the data matrix, F = Nb/2+1 bins.
 struct Dims {
   int Nb, H, K, L, M, J, N, V, d, refA, refB, runA, runB, F, n, ldn, P, Ns, LX;
+  int clean;       // 1: MATLAB data matrix (N-J+1 columns, no skipped sample)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -82,6 +83,8 @@ struct Handle {
   double* ST = nullptr;      // [2][M][N]
   double* Sp = nullptr;      // [4][M][L][Ns]   s' = delete(S, J), zero padded
   double* seed = nullptr;    // [4][L][L][J]    first-row correlations (stats_mode 2)
+  double* norms = nullptr;   // [4] spectral norms of the statistics (loading_mode 1) + power-iteration scratch
+  double* pvec = nullptr;    // [2][4][n] power-iteration vectors
   double* Pbuf = nullptr;    // [4 slices][4][n][ldn] per-microphone partial statistics (DMMA SYRK, tree-summed)
   double* Wg = nullptr;      // [2][M][F]
   double* tframe = nullptr;  // [2][M][Nb]
@@ -113,6 +116,7 @@ int stage_fir(Handle& h, const double* d_inA, const double* d_inB);           //
 int stage_targets(Handle& h, bool compute_gain);                              // S2 + S2b
 int stage_weighted(Handle& h);                                                // S3
 int stage_stats(Handle& h);                                                   // S4 (stats.cu)
+int stage_loading(Handle& h);                                                 // MATLAB diagonal loading (stats.cu)
 int stage_sweep(Handle& h, double mu, double* W_out);                         // S6 (render.cu)
 int stage_render(Handle& h);                                                  // a2 + S7
 int eval_zone(Handle& h, int zone, int T, const double* feeds, const double* signal, double* out3);  // metrics.cu

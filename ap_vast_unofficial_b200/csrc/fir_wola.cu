@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) wola_target_kernel(const double* __restri
       for (int c = 0; c < nchan; ++c) acc += G2[(size_t)c * F + f] / (pc[c] + Ca);
       const double g = sqrt(Cs * Leff * acc);
       wg[f] = g;
-      nrm += g * g;
+      nrm += (normalize == 2 && f > 0 && f < F - 1) ? 2.0 * g * g : g * g;     // 2: norm of the mirrored Nb-bin curve
     }
     nrm = block_sum(nrm, red);
     if (normalize) {

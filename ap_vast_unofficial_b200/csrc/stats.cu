@@ -27,11 +27,20 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
 
+__global__ void fill_const_kernel(double* p, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // s'[e] = S[e < J ? e : e + 1], zero padded to Ns.  grid (4*M*L), one CTA per channel.
-__global__ void pack_stats_kernel(const double* __restrict__ S, double* __restrict__ Sp, int N, int J, int Ns) {
+// clean != 0 (MATLAB data matrix, apVast.m:420-422): no sample is skipped, s' = S.
+__global__ void pack_stats_kernel(const double* __restrict__ S, double* __restrict__ Sp, int N, int J, int Ns, int clean) {
   const double* s = S + (size_t)blockIdx.x * N;
   double* sp = Sp + (size_t)blockIdx.x * Ns;
-  for (int e = threadIdx.x; e < Ns; e += blockDim.x) sp[e] = (e < N - 1) ? s[e < J ? e : e + 1] : 0.0;
+  if (clean) {
+    for (int e = threadIdx.x; e < Ns; e += blockDim.x) sp[e] = (e < N) ? s[e] : 0.0;
+  } else {
+    for (int e = threadIdx.x; e < Ns; e += blockDim.x) sp[e] = (e < N - 1) ? s[e < J ? e : e + 1] : 0.0;
+  }
 }
 
 // Tile list: lower-triangle tiles (bi >= bj) enumerated linearly; blockIdx.y = path.
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(256) rvec_kernel(const double* __restrict__ Sp
   double acc = 0.0;
   for (int m = 0; m < D.M; ++m) {
     const double* sp = Sp + (((size_t)path * D.M + m) * D.L + l) * D.Ns + (D.J - 1 - i);
-    const double* dm = ST + ((size_t)X * D.M + m) * D.N + D.J;
+    const double* dm = ST + ((size_t)X * D.M + m) * D.N + (D.clean ? D.J - 1 : D.J);
     double a = 0.0;
     for (int p = lane; p < D.P; p += 32) a = fma(sp[p], dm[p], a);
     acc += warp_sum(a);
@@ -326,11 +335,83 @@ __global__ void stats_mirror_kernel(double* __restrict__ R, Dims D, unsigned pat
   }
 }
 
+// R, r *= scale (MATLAB normalisation by (N-J+1) M, apVast.m:448-456)
+__global__ void scale_stats_kernel(double* __restrict__ R, double* __restrict__ rvec, size_t nR, size_t nr, double scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nR + nr; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nR) R[i] *= scale;
+    else rvec[i - nR] *= scale;
+  }
+}
+
+// One power-iteration step for the four statistics at once: y = R x, partial |y|^2.  grid (ceil(n/8), 4).
+__global__ void __launch_bounds__(256) power_step_kernel(const double* __restrict__ R, const double* __restrict__ x,
+                                                         double* __restrict__ y, int n, int ldn) {
+  const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  const double* row = R + ((size_t)p * n + r) * ldn;
+  const double* xv = x + (size_t)p * n;
+  double acc = 0.0;
+  for (int k = lane; k < n; k += 32) acc = fma(row[k], xv[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[(size_t)p * n + r] = acc;
+}
+
+// x <- y / |y|, norms[p] = |y| (x has unit norm, so |R x| -> |R|_2), norms[4 + p] = previous estimate.  grid (4).
+__global__ void __launch_bounds__(256) power_norm_kernel(const double* __restrict__ y, double* __restrict__ x,
+                                                         double* __restrict__ norms, int n) {
+  __shared__ double red[40];
+  const int p = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = y[(size_t)p * n + i]; s = fma(v, v, s); }
+  s = sqrt(block_sum(s, red));
+  const double inv = s > 0.0 ? 1.0 / s : 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x[(size_t)p * n + i] = y[(size_t)p * n + i] * inv;
+  if (threadIdx.x == 0) { norms[4 + p] = norms[p]; norms[p] = s; }
+}
+
+// R[p][i][i] += coef[p] * norms[p]   grid (ceil(n/256), 4)
+__global__ void diag_load_kernel(double* __restrict__ R, const double* __restrict__ norms, int n, int ldn,
+                                 double bright, double dark) {
+  const int p = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double coef = (p == 0 || p == 3) ? bright : dark;       // R_A_to_A, R_B_to_B are the bright matrices
+  R[((size_t)p * n + i) * ldn + i] += coef * norms[p];
+}
+
 }  // namespace
+
+// MATLAB diagonalLoading (apVast.m:552-569): spectral norms by power iteration (run to convergence of the estimate),
+// then bright += 1e-8 |R_B|_2 I and dark += 5e-3 |R_D|_2 I on the stored statistics.
+int stage_loading(Handle& h) {
+  const Dims& D = h.D;
+  const int n = D.n;
+  double* x = h.pvec;
+  double* y = h.pvec + 4 * (size_t)n;
+  fill_const_kernel<<<64, 256, 0, h.st>>>(x, 4 * (size_t)n, 1.0 / sqrt((double)n));
+  double hn[8];
+  for (int it = 0; it < 4000; it += 25) {
+    for (int k = 0; k < 25; ++k) {
+      power_step_kernel<<<dim3(ceil_div(n, 8), 4), 256, 0, h.st>>>(h.R, x, y, n, D.ldn);
+      power_norm_kernel<<<4, 256, 0, h.st>>>(y, x, h.norms, n);
+    }
+    h.launches += 50;
+    APV_CUDA_TRY(cudaMemcpyAsync(hn, h.norms, sizeof(hn), cudaMemcpyDeviceToHost, h.st));
+    APV_CUDA_TRY(cudaStreamSynchronize(h.st));
+    bool done = true;
+    for (int p = 0; p < 4; ++p)
+      if (fabs(hn[p] - hn[4 + p]) > 1e-15 * fabs(hn[p])) done = false;
+    if (done) break;
+  }
+  diag_load_kernel<<<dim3(ceil_div(n, 256), 4), 256, 0, h.st>>>(h.R, h.norms, n, D.ldn, h.cfg.bright_load, h.cfg.dark_load);
+  h.launches += 1;
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
 
 int stage_stats(Handle& h) {
   const Dims& D = h.D;
-  pack_stats_kernel<<<4 * D.M * D.L, 256, 0, h.st>>>(h.S, h.Sp, D.N, D.J, D.Ns);
+  pack_stats_kernel<<<4 * D.M * D.L, 256, 0, h.st>>>(h.S, h.Sp, D.N, D.J, D.Ns, D.clean);
   const int nt = ceil_div(D.n, TM);
   const int ntile = nt * (nt + 1) / 2;
   const int SEG = round_up(D.J + KC - 1, 2);
@@ -362,6 +443,11 @@ int stage_stats(Handle& h) {
     APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
     rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
     h.launches += 5;
+    if (h.cfg.normalize_stats) {
+      const double scale = 1.0 / ((double)D.P * (double)D.M);
+      scale_stats_kernel<<<256, 256, 0, h.st>>>(h.R, h.rvec, (size_t)4 * D.n * D.ldn, (size_t)2 * D.n, scale);
+      h.launches += 1;
+    }
     APV_CUDA_TRY(cudaGetLastError());
     return OK;
   }
@@ -376,6 +462,11 @@ int stage_stats(Handle& h) {
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
   rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);
   h.launches += 2 + nl;
+  if (h.cfg.normalize_stats) {
+    const double scale = 1.0 / ((double)D.P * (double)D.M);
+    scale_stats_kernel<<<256, 256, 0, h.st>>>(h.R, h.rvec, (size_t)4 * D.n * D.ldn, (size_t)2 * D.n, scale);
+    h.launches += 1;
+  }
   APV_CUDA_TRY(cudaGetLastError());
   return OK;
 }

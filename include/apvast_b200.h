@@ -58,6 +58,15 @@ typedef struct apv_config {
   double mu;                 /* (:49)                                                               */
   double reg;                /* absolute diagonal loading inside jdiag, reference 1e-7 (:22-24)     */
   double sampling_rate;      /* (:52)                                                               */
+  /* MATLAB-flavoured variant switches (Matlab/ControlMethods/apVast.m; all 0 = the Python reference): */
+  int32_t toeplitz_clean;    /* 1: N-J+1 columns, no skipped sample (apVast.m:420-422)              */
+  int32_t normalize_stats;   /* 1: R, r divided by (N-J+1)*M (apVast.m:448-456)                     */
+  int32_t loading_mode;      /* 0: dark += reg*I inside jdiag (apvast.py:22-24);
+                                1: bright += bright_load*|R_B|_2*I, dark += dark_load*|R_D|_2*I, applied
+                                   to the stored statistics, no further regularisation (apVast.m:552-569) */
+  int32_t target_ref_per_zone; /* 1: target of zone B uses reference_index_B (apVast.m:597-600)     */
+  double bright_load;        /* brightCondLimit, MATLAB 1e-8 (apVast.m:560)                         */
+  double dark_load;          /* darkCondLimit, MATLAB 5e-3 (apVast.m:559)                           */
 } apv_config;
 
 typedef struct apv_handle apv_handle;

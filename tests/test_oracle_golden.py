@@ -66,3 +66,23 @@ def test_full_rank_closed_form():
     n = eng.R_A_to_A.shape[0]
     w = np.linalg.solve(eng.R_A_to_A + eng.mu * (eng.R_A_to_B + 1e-7 * np.eye(n)), eng.r_A)
     assert np.linalg.norm(w - eng.w_A[-1]) / np.linalg.norm(w) < 1e-8
+
+
+def test_matlab_flavour_closed_form():
+    """flavour='matlab' (apVast.m differences): with V = n the last filter is the pressure-matching
+    solution on the LOADED statistics, w = (R_B' + mu R_D')^-1 r_B (apVast.m:115-118, 552-569); no parity pin exists
+    for this flavour (no MATLAB/Octave here), so it is checked through identities only."""
+    rng = np.random.default_rng(8)
+    K, L, M = 20, 3, 2
+    rA = 1e-3 * rng.standard_normal((K, L, M)); rB = 1e-3 * rng.standard_normal((K, L, M))
+    eng = ApvastOracle(64, rA, rB, 6, 2, 0, 2, 18, 0.7, 90, perceptual=False, flavour="matlab")
+    assert np.all(eng.loudspeaker_response_A_to_A_buffer == 0)           # zero start (apVast.m:175-180)
+    for t in range(5):
+        eng.process_input_buffers(rng.standard_normal(32), rng.standard_normal(32))
+    n = 18
+    w = np.linalg.solve(eng.R_B_to_B + 0.7 * eng.R_B_to_A, eng.r_B)
+    assert np.linalg.norm(w - eng.w_B[-1]) / np.linalg.norm(w) < 1e-8
+    assert eng._data_matrix(eng.loudspeaker_weighted_response_A_to_A_buffer, 0).shape == (n, 90 - 6 + 1)
+    # target of zone B sits on loudspeaker reference_index_B
+    ft = eng.filter_spectra_B_t[0]
+    assert np.allclose(np.abs(ft[:, 2]), 1.0) and np.allclose(ft[:, 0], 0.0)
