@@ -20,12 +20,35 @@ namespace {
 constexpr int TM = 128;      // CTA tile (rows = cols)
 constexpr int KC = 64;       // K chunk per pipeline stage
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier transaction counting: one elected thread stages the
+// 1-D segments of a pipeline stage; the copy engine fills shared memory while all warps issue DMMAs.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 __global__ void fill_const_kernel(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -68,7 +91,14 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
   // stage layout: [row segs: maxl*SEG][col segs: maxl*SEG], two stages, then zero segment
   const int stage_sz = 2 * maxl * SEG;
   double* zero_seg = sm + 2 * stage_sz;
+  __shared__ __align__(8) unsigned long long full_bar[2];
   for (int i = threadIdx.x; i < SEG; i += blockDim.x) zero_seg[i] = 0.0;
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
 
   const int lr0 = r0 / J, lr1 = min(L - 1, (r0 + TM - 1) / J);
   const int lc0 = c0 / J, lc1 = min(L - 1, (c0 + TM - 1) / J);
@@ -108,29 +138,24 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
   const size_t chan_stride = (size_t)D.Ns;
   const double* base = Sp + ((size_t)path * D.M + m_first + mslice) * L * chan_stride;
 
+  // one thread stages a pipeline stage: (nlr + nlc) segments of SEG doubles (SEG even, sources 16-byte aligned)
   auto stage_load = [&](int it, int s) {
     const int p0 = it * KC;
     double* dst = sm + s * stage_sz;
     const double* src = base + p0;
-    const int tot_r = nlr * SEG;
-    for (int e = tid; e < tot_r; e += 256) {
-      const int ls = e / SEG, o = e - ls * SEG;
-      cp_async8(dst + e, src + (size_t)(lr0 + ls) * chan_stride + o);
-    }
-    const int tot_c = nlc * SEG;
-    for (int e = tid; e < tot_c; e += 256) {
-      const int ls = e / SEG, o = e - ls * SEG;
-      cp_async8(dst + maxl * SEG + e, src + (size_t)(lc0 + ls) * chan_stride + o);
-    }
-    cp_async_commit();
+    const unsigned seg_bytes = (unsigned)SEG * 8u;
+    mbar_expect_tx(&full_bar[s], (unsigned)(nlr + nlc) * seg_bytes);
+    for (int ls = 0; ls < nlr; ++ls) bulk_g2s(dst + ls * SEG, src + (size_t)(lr0 + ls) * chan_stride, seg_bytes, &full_bar[s]);
+    for (int ls = 0; ls < nlc; ++ls)
+      bulk_g2s(dst + maxl * SEG + ls * SEG, src + (size_t)(lc0 + ls) * chan_stride, seg_bytes, &full_bar[s]);
   };
 
-  stage_load(0, 0);
+  if (tid == 0) stage_load(0, 0);
   for (int it = 0; it < nit; ++it) {
     const int s = it & 1;
-    cp_async_wait_all();
-    __syncthreads();                      // stage s visible; everyone finished reading stage s^1
-    if (it + 1 < nit) stage_load(it + 1, s ^ 1);
+    mbar_wait(&full_bar[s], (unsigned)((it >> 1) & 1));   // stage s has landed
+    __syncthreads();                                      // everyone finished reading stage s^1
+    if (tid == 0 && it + 1 < nit) stage_load(it + 1, s ^ 1);
     const double* st = sm + s * stage_sz;
     const int p0 = (it % nchunk) * KC;
     const int klen = min(KC, P - p0);
