@@ -71,7 +71,10 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 //   transB == 0: B is K x N (ldb);  transB == 1: B is stored N x K (ldb)  (op(B) = B^T)
 //   tri: 0 = all tiles; 1 = only tiles that touch the lower triangle (row >= col) of C;
 //        (elements above the diagonal inside diagonal tiles are still written).
-//   batch: blockIdx.z, operands advance by strideA/B/C elements.
+//   batch: operands advance by strideA/B/C elements per batch entry;
+//   split (> 1): every batch entry holds `split` sub-products (e.g. K slices writing partial results) whose operands
+//        advance by splitA/B/C elements; blockIdx.z = batch index * split + sub-product.  With split_ktot the
+//        sub-products are slices of one K range of that length (the last slice may be short or empty).
 struct GemmArgs {
   const double* A; const double* B; double* C;
   int M, N, K;
@@ -79,6 +82,9 @@ struct GemmArgs {
   long long strideA, strideB, strideC;
   double alpha, beta;
   int transA, transB, tri, batch;
+  int split;
+  long long splitA, splitB, splitC;
+  int split_ktot;   // > 0: sub-product s covers K indices [s K, min((s + 1) K, split_ktot))
 };
 int gemm_f64(const GemmArgs& g, cudaStream_t st);
 

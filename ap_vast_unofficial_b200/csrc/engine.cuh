@@ -39,6 +39,8 @@ struct JdiagWs {
   double* iv = nullptr;     // [nz][6][n][Vp] inverse-iteration work (interleaved over vectors)
   double* Zt = nullptr;     // [nz][V][n] eigenvectors of T -> of C -> joint eigenvectors U (row v)
   int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
+  double* ts2 = nullptr;    // two-stage tridiagonalisation scratch (band.cu): V panel, Y slices, X, S partials, T, band, flags
+  cudaEvent_t ev2[2] = {};  // two-stage: end of stage 1 (dense -> band), end of stage 2 (band -> tridiagonal)
   int Vp = 0;
   size_t bytes = 0;
   cudaEvent_t ev[8] = {};   // phase boundaries: prep | chol | reduce | tridiag | eig | backtransform | solve
@@ -51,6 +53,12 @@ void jdiag_free(JdiagWs& ws);
 // tridiag.cu: Cm -> (dd, ee, VH, tau); uses Z1/Z2/colbuf/tdws.  Adds its kernel launches to *launches.
 int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches);
 size_t tridiag_scratch_doubles(int n, int nz);
+// band.cu (eig_mode 3): Cm -> band (stage-1 reflectors in VH / tau) -> (dd, ee) (stage-2 reflectors in Tm);
+// twostage_apply_q2 maps the eigenvectors of T in the inverse-iteration workspace to those of the band matrix.
+size_t twostage_scratch_bytes(int n, int nz, int nsplit_max);
+int twostage_nsplit_max();
+int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches);
+int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches);
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
               cudaStream_t st, int* launches);
 

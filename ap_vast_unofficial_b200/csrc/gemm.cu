@@ -3,9 +3,12 @@
 // back-transformations).  Replaces the BLAS-3 calls underneath the reference's jdiag
 // (Python/apvast.py:20-36: LAPACK dpotrf/dtrtrs + BLAS dgemm/dsyrk).
 //
-// CTA tile 128x128x16, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA atoms (64 FP64 accumulators/thread),
-// register-staged double buffering of the global->shared copies, padded shared tiles so every
-// fragment load is bank-conflict free (row pitch == 4 mod 16 doubles).
+// CTA tile 128 x BN x 16 (BN = 128, 64 or 32 by the width of the product), 8 warps, warp tile (BM / warps_m) x 32:
+// 64x32 = 8x4 DMMA atoms (64 FP64 accumulators/thread) at BN = 128, 32x32 at BN = 64, 16x32 at BN = 32 (the
+// skinny products of the band reduction, which are bandwidth-bound and run two CTAs per SM).  Register-staged
+// double buffering of the global->shared copies, padded shared tiles so every fragment load is bank-conflict
+// free (row pitch == 4 mod 16 doubles).  blockIdx.z = batch * split + s: `split` independent K-slices or
+// sub-problems inside one batch entry advance the operands by splitA/B/C elements.
 #include "common.cuh"
 
 namespace apv {
@@ -14,11 +17,12 @@ thread_local char g_err[512] = {0};
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int BM = 128, BK = 16;
 constexpr int LDK = BK + 4;    // pitch of [rows][BK] tiles      (20  == 4 mod 16)
-constexpr int LDM = BM + 4;    // pitch of [BK][rows] tiles      (132 == 4 mod 16)
-constexpr int TILE = (BM * LDK > BK * LDM) ? BM * LDK : BK * LDM;   // doubles per operand tile
-constexpr int SMEM_BYTES = 4 * TILE * (int)sizeof(double);          // 2 operands x 2 stages
+constexpr int LDM = BM + 4;    // pitch of [BK][BM] tiles        (132 == 4 mod 16)
+constexpr int TILE_A = (BM * LDK > BK * LDM) ? BM * LDK : BK * LDM;   // doubles per A tile
+__host__ __device__ constexpr int tile_b(int BN) { return (BN * LDK > BK * (BN + 4)) ? BN * LDK : BK * (BN + 4); }
+constexpr int smem_bytes(int BN) { return 2 * (TILE_A + tile_b(BN)) * (int)sizeof(double); }   // 2 stages
 
 // Fetch 8 consecutive doubles of a row-major matrix with bounds (zero fill).
 __device__ __forceinline__ void fetch8(const double* __restrict__ P, int ld, int r, int c, int rmax, int cmax,
@@ -37,54 +41,65 @@ __device__ __forceinline__ void fetch8(const double* __restrict__ P, int ld, int
   }
 }
 
-template <int TA, int TB>
-__global__ void __launch_bounds__(256, 1) gemm_kernel(GemmArgs g) {
+template <int TA, int TB, int BN>
+__global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_kernel(GemmArgs g) {
+  constexpr int WN = BN / 32, WM = 8 / WN, WR = BM / WM, RT = WR / 8;   // warp grid, warp rows, row atoms
+  constexpr int LDN = BN + 4;                                           // pitch of [BK][BN] tiles (== 4 mod 16)
+  constexpr int TILE_B = tile_b(BN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (g.tri && n0 > m0 + BM - 1) return;
   extern __shared__ __align__(16) double smem[];
-  double* As[2] = {smem, smem + TILE};
-  double* Bs[2] = {smem + 2 * TILE, smem + 3 * TILE};
+  double* As[2] = {smem, smem + TILE_A};
+  double* Bs[2] = {smem + 2 * TILE_A, smem + 2 * TILE_A + TILE_B};
 
-  const double* __restrict__ A = g.A + (size_t)blockIdx.z * g.strideA;
-  const double* __restrict__ B = g.B + (size_t)blockIdx.z * g.strideB;
-  double* __restrict__ C = g.C + (size_t)blockIdx.z * g.strideC;
+  const int nsp = g.split > 1 ? g.split : 1;
+  const int zb = blockIdx.z / nsp, zs = blockIdx.z % nsp;
+  const double* __restrict__ A = g.A + (size_t)zb * g.strideA + (size_t)zs * g.splitA;
+  const double* __restrict__ B = g.B + (size_t)zb * g.strideB + (size_t)zs * g.splitB;
+  double* __restrict__ C = g.C + (size_t)zb * g.strideC + (size_t)zs * g.splitC;
+  const int K = g.split_ktot > 0 ? max(0, min(g.K, g.split_ktot - zs * g.K)) : g.K;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp / WN) * WR, wn = (warp % WN) * 32;
   const int gq = lane >> 2, tq = lane & 3;
   const bool vecA = ((g.lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   const bool vecB = ((g.ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
   // global->shared mapping
   //  [rows][BK] tiles: thread -> row tid>>1, cols (tid&1)*8 .. +7
-  //  [BK][rows] tiles: thread -> k-row tid>>4, cols (tid&15)*8 .. +7
+  //  [BK][rows] tiles: thread -> k-row tid / (rows/8), cols (tid % (rows/8))*8 .. +7
+  // (the B tile has BN rows / columns: only the first 2 BN threads carry a piece of it)
   const int rA = TA ? (tid >> 4) : (tid >> 1), cA = TA ? (tid & 15) * 8 : (tid & 1) * 8;
-  const int rB = TB ? (tid >> 1) : (tid >> 4), cB = TB ? (tid & 1) * 8 : (tid & 15) * 8;
+  const int rB = TB ? (tid >> 1) : (tid / (BN / 8)), cB = TB ? (tid & 1) * 8 : (tid % (BN / 8)) * 8;
+  const bool hasB = tid < 2 * BN;
 
   double ra[8], rb[8];
   auto gload = [&](int k0) {
-    if (TA) fetch8(A, g.lda, k0 + rA, m0 + cA, g.K, g.M, vecA, ra);
-    else    fetch8(A, g.lda, m0 + rA, k0 + cA, g.M, g.K, vecA, ra);
-    if (TB) fetch8(B, g.ldb, n0 + rB, k0 + cB, g.N, g.K, vecB, rb);
-    else    fetch8(B, g.ldb, k0 + rB, n0 + cB, g.K, g.N, vecB, rb);
+    if (TA) fetch8(A, g.lda, k0 + rA, m0 + cA, K, g.M, vecA, ra);
+    else    fetch8(A, g.lda, m0 + rA, k0 + cA, g.M, K, vecA, ra);
+    if (hasB) {
+      if (TB) fetch8(B, g.ldb, n0 + rB, k0 + cB, g.N, K, vecB, rb);
+      else    fetch8(B, g.ldb, k0 + rB, n0 + cB, K, g.N, vecB, rb);
+    }
   };
   auto sstore = [&](int s) {
     double* a = As[s] + rA * (TA ? LDM : LDK) + cA;
-    double* b = Bs[s] + rB * (TB ? LDK : LDM) + cB;
+    double* b = Bs[s] + rB * (TB ? LDK : LDN) + cB;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      reinterpret_cast<double2*>(a)[i] = make_double2(ra[2 * i], ra[2 * i + 1]);
-      reinterpret_cast<double2*>(b)[i] = make_double2(rb[2 * i], rb[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(a)[i] = make_double2(ra[2 * i], ra[2 * i + 1]);
+    if (hasB) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(b)[i] = make_double2(rb[2 * i], rb[2 * i + 1]);
     }
   };
 
-  double acc[8][4][2];
+  double acc[RT][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int nk = (g.K + BK - 1) / BK;
+  const int nk = (K + BK - 1) / BK;
   if (nk > 0) {
     gload(0);
     sstore(0);
@@ -97,15 +112,15 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(GemmArgs g) {
     const double* b_s = Bs[s];
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
+      double a[RT], b[4];
 #pragma unroll
-      for (int rt = 0; rt < 8; ++rt)
+      for (int rt = 0; rt < RT; ++rt)
         a[rt] = TA ? a_s[(kk * 4 + tq) * LDM + wm + rt * 8 + gq] : a_s[(wm + rt * 8 + gq) * LDK + kk * 4 + tq];
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct)
-        b[ct] = TB ? b_s[(wn + ct * 8 + gq) * LDK + kk * 4 + tq] : b_s[(kk * 4 + tq) * LDM + wn + ct * 8 + gq];
+        b[ct] = TB ? b_s[(wn + ct * 8 + gq) * LDK + kk * 4 + tq] : b_s[(kk * 4 + tq) * LDN + wn + ct * 8 + gq];
 #pragma unroll
-      for (int rt = 0; rt < 8; ++rt)
+      for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
         for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
     }
@@ -115,7 +130,7 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(GemmArgs g) {
 
   const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
-  for (int rt = 0; rt < 8; ++rt) {
+  for (int rt = 0; rt < RT; ++rt) {
     const int r = m0 + wm + rt * 8 + gq;
     if (r >= g.M) continue;
 #pragma unroll
@@ -138,17 +153,25 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(GemmArgs g) {
   }
 }
 
-template <int TA, int TB>
-int launch(const GemmArgs& g, cudaStream_t st) {
+template <int TA, int TB, int BN>
+int launch_bn(const GemmArgs& g, cudaStream_t st) {
   static thread_local bool configured = false;
   if (!configured) {
-    APV_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    APV_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes(BN)));
     configured = true;
   }
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.batch > 0 ? g.batch : 1);
-  gemm_kernel<TA, TB><<<grid, 256, SMEM_BYTES, st>>>(g);
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), (g.batch > 0 ? g.batch : 1) * (g.split > 1 ? g.split : 1));
+  gemm_kernel<TA, TB, BN><<<grid, 256, smem_bytes(BN), st>>>(g);
   APV_CUDA_TRY(cudaGetLastError());
   return OK;
+}
+
+template <int TA, int TB>
+int launch(const GemmArgs& g, cudaStream_t st) {
+  if (g.N <= 32) return launch_bn<TA, TB, 32>(g, st);
+  if (g.N <= 64) return launch_bn<TA, TB, 64>(g, st);
+  return launch_bn<TA, TB, 128>(g, st);
 }
 
 }  // namespace

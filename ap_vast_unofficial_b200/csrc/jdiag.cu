@@ -903,7 +903,9 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.iv, (size_t)nz * 6 * n * ws.Vp * sizeof(double)));
   APV_TRY(al((void**)&ws.Zt, (size_t)nz * V * n * sizeof(double)));
   APV_TRY(al((void**)&ws.info, (size_t)nz * 4 * sizeof(int)));
+  APV_TRY(al((void**)&ws.ts2, twostage_scratch_bytes(n, nz, twostage_nsplit_max())));
   for (auto& e : ws.ev) APV_CUDA_TRY(cudaEventCreate(&e));
+  for (auto& e : ws.ev2) APV_CUDA_TRY(cudaEventCreate(&e));
   ws.npanel = ceil_div(n, NBT);
   ws.pev = new cudaEvent_t[2 * ws.npanel]();
   for (int i = 0; i < 2 * ws.npanel; ++i) APV_CUDA_TRY(cudaEventCreate(&ws.pev[i]));
@@ -913,10 +915,12 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : ws.ev2)
     if (e) cudaEventDestroy(e);
   if (ws.pev) {
     for (int i = 0; i < 2 * ws.npanel; ++i)
@@ -1057,7 +1061,9 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     if (launches) *launches += nl;
     return OK;
   }
-  APV_TRY(tridiag_run(ws, st, &nl));
+  const bool two_stage = ws.eig_mode == 3;
+  if (two_stage) APV_TRY(twostage_run(ws, st, &nl));
+  else APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));
   // ---- top-V eigenpairs of T
   double* tnorm = ws.shift + (size_t)nz * V;
@@ -1073,6 +1079,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   }
   eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
   APV_CUDA_TRY(cudaEventRecord(ws.ev[4], st));
+  if (two_stage) APV_TRY(twostage_apply_q2(ws, st, &nl));
   APV_TRY(ensure_smem(eig_backtransform_kernel, (size_t)n * sizeof(double)));
   wy_tfactor_kernel<<<dim3(ceil_div(n, WYB), nz), 256, 0, st>>>(ws.VH, ws.tau, ws.Tf, n, ldn);
   eig_backtransform_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.Tf, ws.Zt, n, ldn, V, ws.Vp);

@@ -13,7 +13,8 @@ def _capi():
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 136, 48), (37, 301, 75), (64, 500, 64), (260, 64, 130)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 136, 48), (37, 301, 75), (64, 500, 64), (260, 64, 130),
+                                   (300, 32, 130), (150, 17, 64), (129, 40, 33)])   # skinny tiles (BN = 32 / 64)
 def test_gemm_dmma(ta, tb, M, N, K):
     capi = _capi()
     rng = np.random.default_rng(M * 7 + N * 3 + K + ta * 2 + tb)
@@ -48,7 +49,11 @@ def _spd_pair(n, rng, cols=3):
 
 
 @pytest.mark.parametrize("n,V,eig_mode", [(24, 24, 1), (24, 24, 2), (70, 10, 1), (70, 10, 2), (100, 100, 1), (100, 100, 2),
-                                          (111, 7, 2), (257, 33, 0), (640, 64, 0)])
+                                          (111, 7, 2), (257, 33, 0), (640, 64, 0),
+                                          # eig_mode 3 = two-stage (band reduction + bulge chasing); 24: band only,
+                                          # 34: the smallest panel, 65 / 97: partial last blocks
+                                          (24, 24, 3), (34, 10, 3), (65, 65, 3), (97, 20, 3), (100, 100, 3),
+                                          (257, 33, 3), (640, 64, 3), (1100, 64, 3)])
 def test_jdiag_identities_and_filters(n, V, eig_mode):
     """jdiag.m:33-35 identities and the filter sum against the reference route (oracle jdiag)."""
     from ap_vast_unofficial_b200 import jdiag
@@ -82,7 +87,7 @@ def test_jdiag_not_positive_definite():
         jdiag(A, B, number_of_eigenvectors=4)
 
 
-@pytest.mark.parametrize("eig_mode", [1, 2])
+@pytest.mark.parametrize("eig_mode", [1, 2, 3])
 def test_jdiag_rank_deficient_bright(eig_mode):
     """Degenerate zero eigenvalues (bright matrix of rank 5): the rank-n filter is still the closed form."""
     from ap_vast_unofficial_b200 import jdiag
