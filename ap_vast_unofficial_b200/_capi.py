@@ -67,6 +67,7 @@ SIGNATURES = {
     "apv_util_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, _dp]),
     "apv_util_fft": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
     "apv_bench_dmma_peak": (C.c_int, [C.c_int, _dp]),
+    "apv_bench_dfma": (C.c_int, [C.c_int, _dp]),
     "apv_bench_gemm": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "apv_last_error": (C.c_char_p, []),
     "apv_version": (C.c_char_p, []),

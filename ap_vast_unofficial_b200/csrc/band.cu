@@ -18,6 +18,7 @@
 //     vector, vector in shared memory), then the compact-WY kernel of jdiag.cu with the stage-1 reflectors.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -30,12 +31,11 @@ namespace apv {
 namespace {
 
 constexpr int NB2 = 32;          // half bandwidth of the intermediate band matrix == warp size (one lane per row)
-constexpr int LDB = 2 * NB2;     // band storage: AB[j][d] = A[j + d][j], d = 0 .. 2 NB2 - 1 (band + bulge)
-constexpr int QRT = 256;         // threads of the panel QR CTAs (8 warps, lane = panel column)
+constexpr int LDB = 2 * NB2;     // band storage (row-major): AB[i][e] = A[i][i - e], e = 0 .. 2 NB2 - 1 (band + bulge)
+constexpr int QRT = 1024;        // threads of the panel QR CTAs (32 warps, lane = panel column)
 constexpr int QRW = QRT / 32;
 constexpr int QR_MAXCS = 16;     // largest cluster
 constexpr int PP = NB2 + 1;      // shared-memory pitch of the panel slab (odd: rows and columns conflict-free)
-constexpr int CHT = 128;         // threads of the chase CTAs (4 sweeps per CTA)
 constexpr int PROG_DONE = 0x7fffffff;
 
 // ------------------------------------------------------------------------------------------------
@@ -43,7 +43,10 @@ constexpr int PROG_DONE = 0x7fffffff;
 struct SbPanel {
   double* Cm; double* VH; double* VP; double* tau; double* Tp;
   int n, ldn, j0, rows_per;
+  long long* dbg;      // APV_TS_DEBUG: clock64 totals per phase (rank 0 / warp 0 of zone 0)
 };
+
+#define SB_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (threadIdx.x == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
 
 __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   extern __shared__ __align__(16) double slab[];          // [rows_per][PP]
@@ -52,11 +55,15 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   __shared__ double red[QRW][NB2];
   __shared__ double Gs[NB2][PP];                          // V^T V above the diagonal (rank 0)
   __shared__ double taus[NB2];
+  __shared__ double Tsm[NB2][PP];
+  __shared__ double tqs[NB2], scal[2];                    // tau * (v^T P) per column, {1 / (alpha - beta), beta}
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int z = blockIdx.y, n = a.n, ldn = a.ldn, j0 = a.j0, r = j0 + NB2, npn = n - r;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* Cm = a.Cm + (size_t)z * n * ldn;
+  long long* dbgp = (a.dbg && z == 0 && rank == 0) ? a.dbg : nullptr;
+  long long tk = clock64();
   const int s0 = min(npn, rank * a.rows_per), s1 = min(npn, s0 + a.rows_per), nr = s1 - s0;   // slab rows [s0, s1)
   for (int i = warp; i < nr; i += QRW) slab[i * PP + lane] = Cm[(size_t)(r + s0 + i) * ldn + j0 + lane];
   cluster.sync();             // every CTA of the cluster runs before its shared memory is written remotely
@@ -64,50 +71,75 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   double acc = 0.0;
   for (int i = warp; i < nr; i += QRW)
     if (s0 + i > 0) acc = fma(slab[i * PP + lane], slab[i * PP], acc);
+  SB_TICK(0);
   for (int j = 0; j < NB2; ++j) {
     const int par = j & 1;
     red[warp][lane] = acc;
     __syncthreads();
-    for (int k = warp; k < CS; k += QRW) {      // warp k delivers this CTA's partial to rank k (k + QRW, ..)
-      double t = 0.0;
+    SB_TICK(1);
+    if (warp == 0) {           // one warp sums the CTA's partial Gram row and delivers it to every rank
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-      for (int w = 0; w < QRW; ++w) t += red[w][lane];
-      cluster.map_shared_rank(&xpart[par][rank][0], k)[lane] = t;
-    }
-    if (j >= s0 && j < s1 && warp == QRW - 1) {      // owner of the diagonal row broadcasts it
+      for (int w = 0; w < QRW; w += 4) {
+        t0 += red[w][lane]; t1 += red[w + 1][lane]; t2 += red[w + 2][lane]; t3 += red[w + 3][lane];
+      }
+      const double t = (t0 + t1) + (t2 + t3);
+      for (int k = 0; k < CS; ++k) cluster.map_shared_rank(&xpart[par][rank][0], k)[lane] = t;
+    } else if (warp == 1 && j >= s0 && j < s1) {      // owner of the diagonal row broadcasts it
       const double v = slab[(j - s0) * PP + lane];
       for (int k = 0; k < CS; ++k) cluster.map_shared_rank(&xrow[par][0], k)[lane] = v;
     }
+    SB_TICK(2);
     cluster.sync();
-    double g = 0.0;
-    for (int k = 0; k < CS; ++k) g += xpart[par][k][lane];
-    const double rowj = (j < npn) ? xrow[par][lane] : 0.0;      // (no diagonal row: the column is empty)
-    const double alpha = __shfl_sync(0xffffffffu, rowj, j), sigma = __shfl_sync(0xffffffffu, g, j);
-    double beta = alpha, tau = 0.0, scale = 0.0;
-    if (sigma > 0.0 && j < npn - 1) {
-      beta = -copysign(hypot(alpha, sqrt(sigma)), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
+    SB_TICK(3);
+    if (warp == 0) {           // reflector scalars once per CTA (32 warps doing this redundantly fill the FP64 pipe)
+      double g = 0.0;
+      for (int k = 0; k < CS; ++k) g += xpart[par][k][lane];
+      const double rowj = (j < npn) ? xrow[par][lane] : 0.0;      // (no diagonal row: the column is empty)
+      const double alpha = __shfl_sync(0xffffffffu, rowj, j), sigma = __shfl_sync(0xffffffffu, g, j);
+      double beta = alpha, tau = 0.0, scale = 0.0;
+      if (sigma > 0.0 && j < npn - 1) {
+        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      const double q = fma(scale, g, rowj);     // lane > j: (v^T P)[lane];  lane < j: (V^T V)[lane][j]
+      tqs[lane] = tau * q;
+      if (lane == 0) { scal[0] = scale; scal[1] = beta; }
+      if (rank == 0) {
+        if (lane < j) Gs[lane][j] = q;
+        if (lane == j) taus[j] = tau;
+      }
     }
-    const double q = fma(scale, g, rowj);     // lane > j: (v^T P)[lane];  lane < j: (V^T V)[lane][j]
-    if (rank == 0 && warp == 0) {
-      if (lane < j) Gs[lane][j] = q;
-      if (lane == j) taus[j] = tau;
-    }
+    __syncthreads();
+    const double scale = scal[0], beta = scal[1], tq = tqs[lane];
+    SB_TICK(4);
     // update of the rows below the diagonal fused with the partial Gram row of column j + 1
-    acc = 0.0;
-    const double tq = tau * q;
-    for (int i = warp; i < nr; i += QRW) {
-      const int gr = s0 + i;
-      if (gr <= j) continue;
-      double x = slab[i * PP + lane];
-      const double vr = slab[i * PP + j] * scale;
-      if (lane > j) x = fma(-vr, tq, x);
-      else if (lane == j) x = vr;
-      if (lane >= j) slab[i * PP + lane] = x;
-      const double xb = __shfl_sync(0xffffffffu, x, (j + 1) & 31);
-      if (gr > j + 1) acc = fma(x, xb, acc);
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    // rows of this warp: i = warp + QRW t; the rows gr = s0 + i <= j (leading rows of the first slabs) are finished
+    int i = warp;
+    if (s0 + i <= j) i += ((j - s0 - i) / QRW + 1) * QRW;
+    for (; i < nr; i += 4 * QRW) {
+      double x[4], pj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + u * QRW;
+        const bool ok = ii < nr;
+        x[u] = ok ? slab[ii * PP + lane] : 0.0;
+        pj[u] = ok ? slab[ii * PP + j] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + u * QRW;
+        const double vr = pj[u] * scale;
+        if (lane > j) x[u] = fma(-vr, tq, x[u]);
+        else if (lane == j) x[u] = vr;
+        if (ii < nr && lane >= j) slab[ii * PP + lane] = x[u];
+        const double xb = __shfl_sync(0xffffffffu, x[u], (j + 1) & 31);
+        if (s0 + ii > j + 1) a4[u] = fma(x[u], xb, a4[u]);       // (rows beyond the slab hold zeros)
+      }
     }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     if (j >= s0 && j < s1 && warp == 0) {            // diagonal row: R
       double x = slab[(j - s0) * PP + lane];
       if (lane > j) x -= tq;
@@ -115,6 +147,7 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       slab[(j - s0) * PP + lane] = x;
     }
     // (the next iteration's barriers order these writes before any other warp reads them)
+    SB_TICK(5);
   }
   __syncthreads();
   // outputs: R (and zeros) into the panel of C, explicit V (row-major panel and as rows of VH)
@@ -135,19 +168,17 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
     if (warp == 0) {
       a.tau[(size_t)z * n + j0 + lane] = taus[lane];
       // T (dlarft, forward / columnwise): lane = row of T;  T[r][i] = -tau_i sum_{k=r}^{i-1} T[r][k] G[k][i]
-      double T[NB2];
       double* Tp = a.Tp + (size_t)z * NB2 * NB2;
-#pragma unroll
       for (int i = 0; i < NB2; ++i) {
         double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k)
-          if (k >= lane) t = fma(T[k], Gs[k][i], t);
-        T[i] = (lane == i) ? taus[i] : (lane < i ? -taus[i] * t : 0.0);
-        Tp[lane * NB2 + i] = T[i];
+        for (int k = lane; k < i; ++k) t = fma(Tsm[lane][k], Gs[k][i], t);
+        const double v = (lane == i) ? taus[i] : (lane < i ? -taus[i] * t : 0.0);
+        Tsm[lane][i] = v;          // (row `lane` is private to this lane)
+        Tp[lane * NB2 + i] = v;
       }
     }
   }
+  SB_TICK(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,58 +239,70 @@ __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
   for (int c = 0; c < 4; ++c) sp[c] = s4[c];
 }
 
-// W = X - V (1/2 T^T S),  S = sum of the partials;  Z1 = [V | W], Z2 = [W | V].
-__global__ void __launch_bounds__(256) sb_w2_kernel(SbW a) {
+// W = X - V (1/2 T^T S),  S = sum of the partials;  Z1 = [V | W], Z2 = [W | V].   1024 threads (one entry of S each).
+__global__ void __launch_bounds__(1024) sb_w2_kernel(SbW a) {
   __shared__ double Ss[NB2][PP], Ms[NB2][PP], Ts[NB2][PP], Vs[64][PP];
-  const int z = blockIdx.y, blk = blockIdx.x, n = a.n;
-  for (int i = threadIdx.x; i < NB2 * NB2; i += 256) {
-    double s = 0.0;
-    const double* sp = a.Spart + (size_t)z * a.nblk * NB2 * NB2 + i;
-    for (int b = 0; b < a.nblk; ++b) s += sp[(size_t)b * NB2 * NB2];
-    Ss[i / NB2][i % NB2] = s;
-    Ts[i / NB2][i % NB2] = a.Tp[(size_t)z * NB2 * NB2 + i];
+  const int z = blockIdx.y, blk = blockIdx.x, n = a.n, t = threadIdx.x;
+  {
+    const double* sp = a.Spart + (size_t)z * a.nblk * NB2 * NB2 + t;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < a.nblk; b += 4) {
+      s0 += sp[(size_t)b * NB2 * NB2];
+      s1 += sp[(size_t)(b + 1) * NB2 * NB2];
+      s2 += sp[(size_t)(b + 2) * NB2 * NB2];
+      s3 += sp[(size_t)(b + 3) * NB2 * NB2];
+    }
+    for (; b < a.nblk; ++b) s0 += sp[(size_t)b * NB2 * NB2];
+    Ss[t / NB2][t % NB2] = (s0 + s1) + (s2 + s3);
+    Ts[t / NB2][t % NB2] = a.Tp[(size_t)z * NB2 * NB2 + t];
   }
-  const int row = threadIdx.x >> 2, cq = (threadIdx.x & 3) * 8;
+  const int row = t >> 4, cq = (t & 15) * 2;          // 64 rows x 16 column pairs
   const int gr = a.r + blk * 64 + row;
   const bool ok = gr < n;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) Vs[row][cq + c] = ok ? a.VP[((size_t)z * n + gr) * NB2 + cq + c] : 0.0;
+  double x0 = 0.0, x1 = 0.0;
+  if (ok) {
+    const double2 xv = *reinterpret_cast<const double2*>(a.X + ((size_t)z * n + gr) * NB2 + cq);
+    const double2 vv = *reinterpret_cast<const double2*>(a.VP + ((size_t)z * n + gr) * NB2 + cq);
+    x0 = xv.x; x1 = xv.y;
+    Vs[row][cq] = vv.x; Vs[row][cq + 1] = vv.y;
+  } else {
+    Vs[row][cq] = 0.0; Vs[row][cq + 1] = 0.0;
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < NB2 * NB2; i += 256) {
-    const int p = i / NB2, c = i % NB2;
+  {
+    const int p = t / NB2, c = t % NB2;
     double m = 0.0;
     for (int k = 0; k <= p; ++k) m = fma(Ts[k][p], Ss[k][c], m);       // (T^T S)[p][c]
     Ms[p][c] = 0.5 * m;
   }
   __syncthreads();
   if (!ok) return;
-  double w[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) w[c] = a.X[((size_t)z * n + gr) * NB2 + cq + c];
+#pragma unroll 8
   for (int p = 0; p < NB2; ++p) {
     const double v = Vs[row][p];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) w[c] = fma(-v, Ms[p][cq + c], w[c]);
+    x0 = fma(-v, Ms[p][cq], x0);
+    x1 = fma(-v, Ms[p][cq + 1], x1);
   }
   double* z1 = a.Z1 + ((size_t)z * n + gr) * 2 * NB2;
   double* z2 = a.Z2 + ((size_t)z * n + gr) * 2 * NB2;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const double v = Vs[row][cq + c];
-    z1[cq + c] = v; z1[NB2 + cq + c] = w[c];
-    z2[cq + c] = w[c]; z2[NB2 + cq + c] = v;
-  }
+  const double2 vv = make_double2(Vs[row][cq], Vs[row][cq + 1]), ww = make_double2(x0, x1);
+  *reinterpret_cast<double2*>(z1 + cq) = vv;
+  *reinterpret_cast<double2*>(z1 + NB2 + cq) = ww;
+  *reinterpret_cast<double2*>(z2 + cq) = ww;
+  *reinterpret_cast<double2*>(z2 + NB2 + cq) = vv;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Band storage for stage 2: AB[j][d] = C[j + d][j] for d <= NB2 (lower band), zero for the bulge region.
+// Band storage for stage 2, row-major: AB[i][e] = C[i][i - e], e = 0 .. 2 NB2 - 1 (row i to the left of its diagonal
+// element: the band for e <= NB2, room for the bulge beyond), zero outside the matrix.
 __global__ void sb_extract_band_kernel(const double* __restrict__ Cm, double* __restrict__ AB, int n, int ldn) {
   const int z = blockIdx.y;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * LDB) return;
-  const int j = (int)(t / LDB), d = (int)(t % LDB);
+  const int i = (int)(t / LDB), e = (int)(t % LDB);
   double v = 0.0;
-  if (d <= NB2 && j + d < n) v = Cm[(size_t)z * n * ldn + (size_t)(j + d) * ldn + j];
+  if (e <= NB2 && i - e >= 0) v = Cm[(size_t)z * n * ldn + (size_t)i * ldn + (i - e)];
   AB[(size_t)z * n * LDB + t] = v;
 }
 
@@ -268,16 +311,31 @@ __global__ void sb_extract_tridiag_kernel(const double* __restrict__ AB, double*
   const int z = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   dd[(size_t)z * n + j] = AB[((size_t)z * n + j) * LDB];
-  ee[(size_t)z * n + j] = (j + 1 < n) ? AB[((size_t)z * n + j) * LDB + 1] : 0.0;
+  ee[(size_t)z * n + j] = (j + 1 < n) ? AB[((size_t)z * n + j + 1) * LDB + 1] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Stage 2: bulge chasing.  Sweep s annihilates column s of the band below the sub-diagonal with a reflector on
-// rows [s+1, s+1+NB2) and chases the bulge down the band in steps of NB2 rows; every step k >= 1 works on the
-// off-diagonal block B = A[q0:q0+NB2, r0:r0+NB2] (q0 = r0 + NB2) and the diagonal block D = A[q0:, q0:]:
+// rows [s+1, s+1+NB2) and chases the bulge down the band in steps of NB2 rows; step k >= 1 of sweep s works on the
+// rows [q0, q0+NB2), q0 = s+1+k NB2: the off-diagonal block B = A[q0:, r0:q0] (r0 = q0 - NB2) and the diagonal
+// block D = A[q0:, q0:]:
 //     B <- B H_prev;  new reflector H' from B[:, 0];  B[:, 1:] <- H' B[:, 1:];  D <- H' D H'.
-// One warp per sweep, lane = row of the blocks (32 + 32 doubles per lane in registers), vectors are broadcast
-// through a per-warp shared line, column sums use a butterfly transpose-reduction.
+// Step (s+1, k) may run once (s, k+1) is done, so consecutive sweeps follow each other two steps apart and the
+// critical path is 2 n dependent steps: the step latency is everything.  A CTA therefore owns a GROUP of CGW
+// consecutive sweeps, one warp per sweep, running as a wavefront (warp w is at step tau - 2 w in time step tau) on
+// a sliding window of band ROWS kept in shared memory: inside a group a hand-over costs one __syncthreads instead of
+// a round trip through L2.  In one time step the warps touch disjoint rows.  A fifth warp streams the window: it
+// loads the 32 rows the leading sweep needs next (after the previous group has published them), writes back the
+// rows the trailing sweep has finished and publishes the group's row bound (release / acquire counters in global
+// memory); both overlap the compute warps' step.  One warp per step: lane = row of the blocks (32 + 32 doubles per
+// lane in registers), vectors are broadcast through a per-warp shared line, column sums use a butterfly
+// transpose-reduction.
+constexpr int CGW = 3;                        // sweeps per group
+constexpr int CG_NSLOT = 256;                 // window rows (power of two)
+constexpr int CG_PITCH = LDB + 2;             // 66: 16-byte aligned rows, lane stride 67 -> conflict-free block access
+constexpr int CG_THREADS = (CGW + 1) * 32;
+static_assert(63 * CGW - 31 + NB2 <= CG_NSLOT, "window too small");   // live rows of a time step + the chunk in flight
+
 __device__ __forceinline__ void bcast_store(double* line, double v, int lane) {
   __syncwarp();
   line[lane] = v;
@@ -306,23 +364,26 @@ __device__ __forceinline__ void warp_house(double x, int lane, double& v, double
   if (ss == 0.0) {
     beta = alpha; tau = 0.0; v = (lane == 0) ? 1.0 : 0.0;
   } else {
-    beta = -copysign(hypot(alpha, sqrt(ss)), alpha);
+    beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
     tau = (beta - alpha) / beta;
-    v = (lane == 0) ? 1.0 : x / (alpha - beta);
+    v = (lane == 0) ? 1.0 : x * (1.0 / (alpha - beta));
   }
 }
 
 // D <- H D H for the symmetric block whose row `lane` is in D[] (full rows); v, tau = reflector; line = 2 x 32 doubles.
 __device__ __forceinline__ void two_sided32(double (&D)[32], double v, double tau, int lane, double* line) {
   bcast_store(line, v, lane);
-  double p = 0.0;
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    const double2 vv = *reinterpret_cast<const double2*>(line + c);
-    p = fma(D[c], vv.x, p);
-    p = fma(D[c + 1], vv.y, p);
+  for (int c = 0; c < 32; c += 4) {
+    const double2 va = *reinterpret_cast<const double2*>(line + c);
+    const double2 vb = *reinterpret_cast<const double2*>(line + c + 2);
+    p0 = fma(D[c], va.x, p0);
+    p1 = fma(D[c + 1], va.y, p1);
+    p2 = fma(D[c + 2], vb.x, p2);
+    p3 = fma(D[c + 3], vb.y, p3);
   }
-  p *= tau;
+  const double p = tau * ((p0 + p1) + (p2 + p3));
   const double gamma = 0.5 * tau * warp_sum(p * v);
   const double w = p - gamma * v;
   line[32 + lane] = w;
@@ -337,126 +398,203 @@ __device__ __forceinline__ void two_sided32(double (&D)[32], double v, double ta
 }
 
 struct SbChase {
-  double* AB; double* V2; int* prog;
+  double* AB; double* V2; int* gprog;
   int n, ldn, nz;
+  long long* dbg;      // APV_TS_DEBUG: clock64 totals of CTA 0 (compute step / barrier wait; loader store / wait / load)
 };
+#define CH_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (lane == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
+#define CS_TICK(k) do { if (dbgp && wib == 0) { const long long _t = clock64(); if (lane == 0) a.dbg[16 + k] += _t - ts; ts = _t; } } while (0)
 
-__device__ __forceinline__ void chase_load_diag(const double* __restrict__ AB, int n, int q0, int lane, double (&D)[32]) {
-  const int row = q0 + lane;
+__device__ __forceinline__ int sweep_steps(int n, int s) { return (s <= n - 3) ? 1 + (n - s - 2) / NB2 : 0; }
+
+__device__ __forceinline__ double* win_row(double* win, int i) { return win + (size_t)(i & (CG_NSLOT - 1)) * CG_PITCH; }
+
+// Row `lane` of the diagonal block at q0 from the window: own row to the left of the diagonal, the rest by symmetry.
+__device__ __forceinline__ void win_load_diag(double* win, int q0, int lane, double (&D)[32]) {
+  const double* pd = win_row(win, q0 + lane) + lane;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const int col = q0 + c;
-    double v = 0.0;
-    if (row < n && col < n) {
-      v = (c <= lane) ? __ldcg(AB + (size_t)col * LDB + (lane - c)) : __ldcg(AB + (size_t)row * LDB + (c - lane));
-    }
-    D[c] = v;
-  }
+  for (int c = 0; c < 32; ++c) D[c] = (c <= lane) ? pd[-c] : win_row(win, q0 + c)[c - lane];
 }
 
-__device__ __forceinline__ void chase_store_diag(double* __restrict__ AB, int n, int q0, int lane, const double (&D)[32]) {
-  const int row = q0 + lane;
+__device__ __forceinline__ void win_store_diag(double* win, int q0, int lane, const double (&D)[32]) {
+  double* pd = win_row(win, q0 + lane) + lane;
 #pragma unroll
   for (int c = 0; c < 32; ++c)
-    if (c <= lane && row < n) AB[(size_t)(q0 + c) * LDB + (lane - c)] = D[c];
+    if (c <= lane) pd[-c] = D[c];
 }
 
-__device__ __forceinline__ void chase_wait(const int* prog, int s, int need, int lane) {
-  if (s > 0) {
-    if (lane == 0) {
-      const volatile int* p = prog + (s - 1);
-      while (*p < need) {
-      }
-      __threadfence();
-    }
-    __syncwarp();
-  }
-}
-
-__device__ __forceinline__ void chase_post(int* prog, int s, int done, int lane) {
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile int*>(prog + s) = done;
-}
-
-__global__ void __launch_bounds__(CHT, 1) sb2st_chase_kernel(SbChase a) {
-  __shared__ __align__(16) double lines[CHT / 32][64];
+__global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
+  extern __shared__ __align__(16) double win[];                  // [CG_NSLOT][CG_PITCH] rows of the band
+  __shared__ __align__(16) double lines[CGW][64];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nz = a.nz, z = blockIdx.x % nz, n = a.n;
-  const int gw = (blockIdx.x / nz) * (CHT / 32) + wib, G = (gridDim.x / nz) * (CHT / 32);
-  double* line = lines[wib];
+  const int cta = blockIdx.x / nz, G = gridDim.x / nz;
   double* AB = a.AB + (size_t)z * n * LDB;
   double* V2 = a.V2 + (size_t)z * n * a.ldn;
-  int* prog = a.prog + (size_t)z * n;
-  for (int s = gw; s <= n - 3; s += G) {
-    const int nsteps = 1 + (n - s - 2) / NB2;
-    // ---- step 0: reflector of column s, two-sided update of the first diagonal block
-    chase_wait(prog, s, 2, lane);
-    int r0 = s + 1;
-    double D[32];
-    chase_load_diag(AB, n, r0, lane, D);
-    const double x = (r0 + lane < n) ? __ldcg(AB + (size_t)s * LDB + 1 + lane) : 0.0;
-    double v, tau, beta;
-    warp_house(x, lane, v, tau, beta);
-    if (lane == 0) AB[(size_t)s * LDB + 1] = beta;
-    two_sided32(D, v, tau, lane, line);
-    chase_store_diag(AB, n, r0, lane, D);
-    if (r0 + lane < n) V2[(size_t)s * a.ldn + r0 + lane] = (lane == 0) ? tau : v;
-    chase_post(prog, s, nsteps == 1 ? PROG_DONE : 1, lane);
-    // ---- steps k >= 1
-    for (int k = 1; k < nsteps; ++k) {
-      const int q0 = r0 + NB2;
-      chase_wait(prog, s, k + 2, lane);
-      double B[32];
-      const int row = q0 + lane;
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        B[c] = (row < n) ? __ldcg(AB + (size_t)(r0 + c) * LDB + (NB2 + lane - c)) : 0.0;
-      chase_load_diag(AB, n, q0, lane, D);
-      // B <- B H_prev
-      bcast_store(line, v, lane);
-      double y = 0.0;
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const double2 vv = *reinterpret_cast<const double2*>(line + c);
-        y = fma(B[c], vv.x, y);
-        y = fma(B[c + 1], vv.y, y);
-      }
-      y *= tau;
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const double2 vv = *reinterpret_cast<const double2*>(line + c);
-        B[c] = fma(-y, vv.x, B[c]);
-        B[c + 1] = fma(-y, vv.y, B[c + 1]);
-      }
-      // new reflector from the first column of B
-      warp_house(B[0], lane, v, tau, beta);
-      B[0] = (lane == 0) ? beta : 0.0;
-      // B[:, 1:] <- H' B[:, 1:]
-      {
-        double vals[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) vals[c] = v * B[c];
-        const double u = tau * colsum32(vals, lane);       // lane c: tau v^T B[:, c]
-        bcast_store(line, u, lane);
-#pragma unroll
-        for (int c = 2; c < 32; c += 2) {
-          const double2 uu = *reinterpret_cast<const double2*>(line + c);
-          B[c] = fma(-v, uu.x, B[c]);
-          B[c + 1] = fma(-v, uu.y, B[c + 1]);
+  const int ngroups = (n - 2 + CGW - 1) / CGW;
+  int* gprog = a.gprog + (size_t)z * ngroups;
+  long long* dbgp = nullptr;
+  long long tk = clock64();
+
+  // loader: rows [i0, i0 + 32) of the band -> window (zero rows beyond the matrix) once the previous group is past them
+  auto load_chunk = [&](int g, int i0) {
+    if (g > 0 && i0 < n) {
+      const int need = min(n, i0 + NB2);
+      if (lane == 0) {
+        // relaxed polling with back-off (an acquire load per iteration invalidates L1 every time and slows the
+        // compute warps' shared-memory traffic), one acquire fence when the bound is reached
+        int v;
+        for (;;) {
+          asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gprog + (g - 1)) : "memory");
+          if (v >= need) break;
+          __nanosleep(64);
         }
-        B[1] = fma(-v, line[1], B[1]);
+        __threadfence();
       }
-      if (row < n) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) AB[(size_t)(r0 + c) * LDB + (NB2 + lane - c)] = B[c];
-      }
-      two_sided32(D, v, tau, lane, line);
-      chase_store_diag(AB, n, q0, lane, D);
-      if (row < n) V2[(size_t)s * a.ldn + row] = (lane == 0) ? tau : v;
-      chase_post(prog, s, k + 1 == nsteps ? PROG_DONE : k + 1, lane);
-      r0 = q0;
+      __syncwarp();
     }
+    CH_TICK(1);
+    double2 buf[8];
+    for (int r8 = 0; r8 < NB2; r8 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + r8 + u;
+        buf[u] = (i < n) ? __ldcg(reinterpret_cast<const double2*>(AB + (size_t)i * LDB) + lane) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) reinterpret_cast<double2*>(win_row(win, i0 + r8 + u))[lane] = buf[u];
+    }
+    CH_TICK(2);
+  };
+  // loader: window rows [y0, y1) -> global, then publish the bound
+  auto store_rows = [&](int g, int y0, int y1, int publish) {
+    for (int i = y0; i < y1; ++i)
+      reinterpret_cast<double2*>(AB + (size_t)i * LDB)[lane] = reinterpret_cast<const double2*>(win_row(win, i))[lane];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gprog + g), "r"(publish) : "memory");
+    CH_TICK(0);
+  };
+
+  for (int g = cta; g < ngroups; g += G) {
+    // debug clocks: the first group only (it never waits for a predecessor: the unthrottled pace of one time step)
+    dbgp = (a.dbg && blockIdx.x == 0 && g == 0 && (wib == 0 || wib == CGW)) ? a.dbg + 8 + (wib == CGW ? 4 : 0) : nullptr;
+    tk = clock64();
+    const int s0 = g * CGW;
+    const int nst0 = sweep_steps(n, s0);
+    int T = 0;
+#pragma unroll
+    for (int w = 0; w < CGW; ++w) {
+      const int ns = sweep_steps(n, s0 + w);
+      if (ns > 0) T = max(T, ns + 2 * w);
+    }
+    if (wib == CGW) load_chunk(g, s0 + 1);
+    __syncthreads();
+    // compute-warp state carried from step to step
+    const int s = s0 + wib;
+    const int nst = (wib < CGW) ? sweep_steps(n, s) : 0;
+    double v = 0.0, tau = 0.0, beta = 0.0;
+    int ystored = s0 + 1;                       // loader: rows below are back in global memory
+    for (int t = 0; t < T; ++t) {
+      if (wib < CGW) {
+        const int k = t - 2 * wib;
+        if (k == 0 && nst > 0) {
+          // ---- step 0: reflector of column s, two-sided update of the first diagonal block
+          const int r0 = s + 1;
+          double D[32];
+          win_load_diag(win, r0, lane, D);
+          double* myrow = win_row(win, r0 + lane);
+          const double x = myrow[1 + lane];              // A[s+1+lane][s]
+          warp_house(x, lane, v, tau, beta);
+          if (lane == 0) myrow[1] = beta;
+          two_sided32(D, v, tau, lane, lines[wib]);
+          win_store_diag(win, r0, lane, D);
+          if (r0 + lane < n) V2[(size_t)s * a.ldn + r0 + lane] = (lane == 0) ? tau : v;
+        } else if (k > 0 && k < nst) {
+          const int q0 = s + 1 + k * NB2;
+          double* line = lines[wib];
+          double B[32], D[32];
+          long long ts = clock64();
+          double* pb = win_row(win, q0 + lane) + NB2 + lane;      // B(lane, c) = pb[-c]
+#pragma unroll
+          for (int c = 0; c < 32; ++c) B[c] = pb[-c];
+          win_load_diag(win, q0, lane, D);
+          // B <- B H_prev
+          bcast_store(line, v, lane);
+          CS_TICK(0);
+          double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const double2 va = *reinterpret_cast<const double2*>(line + c);
+            const double2 vb = *reinterpret_cast<const double2*>(line + c + 2);
+            y0 = fma(B[c], va.x, y0);
+            y1 = fma(B[c + 1], va.y, y1);
+            y2 = fma(B[c + 2], vb.x, y2);
+            y3 = fma(B[c + 3], vb.y, y3);
+          }
+          const double y = tau * ((y0 + y1) + (y2 + y3));
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const double2 vv = *reinterpret_cast<const double2*>(line + c);
+            B[c] = fma(-y, vv.x, B[c]);
+            B[c + 1] = fma(-y, vv.y, B[c + 1]);
+          }
+          CS_TICK(1);
+          // new reflector from the first column of B
+          warp_house(B[0], lane, v, tau, beta);
+          B[0] = (lane == 0) ? beta : 0.0;
+          CS_TICK(2);
+          // B[:, 1:] <- H' B[:, 1:]
+          {
+            double vals[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) vals[c] = v * B[c];
+            const double u = tau * colsum32(vals, lane);       // lane c: tau v^T B[:, c]
+            bcast_store(line, u, lane);
+#pragma unroll
+            for (int c = 2; c < 32; c += 2) {
+              const double2 uu = *reinterpret_cast<const double2*>(line + c);
+              B[c] = fma(-v, uu.x, B[c]);
+              B[c + 1] = fma(-v, uu.y, B[c + 1]);
+            }
+            B[1] = fma(-v, line[1], B[1]);
+          }
+          CS_TICK(3);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pb[-c] = B[c];
+          CS_TICK(4);
+          two_sided32(D, v, tau, lane, line);
+          CS_TICK(5);
+          win_store_diag(win, q0, lane, D);
+          CS_TICK(6);
+          if (q0 + lane < n) V2[(size_t)s * a.ldn + q0 + lane] = (lane == 0) ? tau : v;
+        }
+        CH_TICK(0);
+      } else {
+        // ---- loader warp: write back what time step t - 1 finished, fetch what time step t + 1 needs
+        if (t > 0) {
+          int ynew = n, remaining = 0;
+#pragma unroll
+          for (int w = 0; w < CGW; ++w) {
+            const int kdone = t - 1 - 2 * w, ns = sweep_steps(n, s0 + w);
+            if (ns > 0 && kdone + 1 < ns) {
+              remaining = 1;
+              ynew = min(ynew, s0 + w + 1 + NB2 * max(kdone + 1, 0));
+            }
+          }
+          ynew = min(ynew, n);
+          if (ynew > ystored) {
+            store_rows(g, ystored, ynew, remaining ? ynew : PROG_DONE);
+            ystored = ynew;
+          }
+        }
+        if (t + 1 <= nst0) load_chunk(g, s0 + 1 + (t + 1) * NB2);
+      }
+      __syncthreads();
+      CH_TICK(3);
+    }
+    if (wib == CGW) store_rows(g, ystored, min(n, s0 + 1 + (nst0 + 1) * NB2), PROG_DONE);
+    __syncthreads();
   }
 }
 
@@ -520,8 +658,33 @@ size_t twostage_scratch_bytes(int n, int nz, int nsplit_max) {
 
 int twostage_nsplit_max() { return 8; }
 
+// APV_TS_DEBUG=1: synchronous per-kernel-class timing of the two-stage reduction, printed to stderr.
+struct TsDebug {
+  bool on = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void begin(cudaStream_t st) { if (on) cudaEventRecord(e0, st); }
+  void end(cudaStream_t st, int k) {
+    if (!on) return;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    acc[k] += ms;
+  }
+};
+
 int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   const int n = ws.n, ldn = ws.ldn, nz = ws.nz;
+  TsDebug dbg;
+  static long long* dclk = nullptr;
+  if (getenv("APV_TS_DEBUG")) {
+    dbg.on = true;
+    cudaEventCreate(&dbg.e0);
+    cudaEventCreate(&dbg.e1);
+    if (!dclk) cudaMalloc((void**)&dclk, 32 * sizeof(long long));
+    cudaMemsetAsync(dclk, 0, 32 * sizeof(long long), st);
+  }
   const long long mstride = (long long)n * ldn;
   const int nsm = twostage_nsplit_max();
   double* VP = ws.ts2;
@@ -541,7 +704,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) {
     const int r = j0 + NB2, npn = n - r;
     // cluster size: smallest of 1, 2, 4, 8, 16 whose slab fits in shared memory
-    const int max_rows = (200 * 1024) / (PP * (int)sizeof(double));
+    const int max_rows = (184 * 1024) / (PP * (int)sizeof(double));
     int CS = 1;
     while (CS < QR_MAXCS && ceil_div(npn, CS) > max_rows) CS *= 2;
     if (npn > 64) CS = std::max(CS, 8);                       // spread the rows anyway: the column loop is latency-bound
@@ -551,14 +714,14 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     }
     SbPanel p;
     p.Cm = ws.Cm; p.VH = ws.VH; p.VP = VP; p.tau = ws.tau; p.Tp = Tp;
-    p.n = n; p.ldn = ldn; p.j0 = j0; p.rows_per = ceil_div(npn, CS);
+    p.n = n; p.ldn = ldn; p.j0 = j0; p.rows_per = ceil_div(npn, CS); p.dbg = dbg.on ? dclk : nullptr;
     const size_t smem = (size_t)p.rows_per * PP * sizeof(double);
     static thread_local size_t configured = 0;
     if (smem > configured) {
       APV_CUDA_TRY(cudaFuncSetAttribute(sb_panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)std::max(smem, (size_t)(200 * 1024))));
+                                        (int)std::max(smem, (size_t)(184 * 1024))));
       APV_CUDA_TRY(cudaFuncSetAttribute(sb_panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = std::max(smem, (size_t)(200 * 1024));
+      configured = std::max(smem, (size_t)(184 * 1024));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, nz); cfg.blockDim = dim3(QRT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -566,7 +729,9 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    dbg.begin(st);
     APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel, p));
+    dbg.end(st, 0);
     ++*launches;
     // Y = C22 V in K slices
     int nsplit = std::max(1, std::min(nsm, (2 * sms) / std::max(1, nz * ceil_div(npn, 128))));
@@ -578,13 +743,17 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     y.B = VP + (size_t)r * NB2; y.ldb = NB2; y.strideB = (long long)n * NB2; y.splitB = (long long)kslice * NB2;
     y.C = Ypart + (size_t)r * NB2; y.ldc = NB2; y.strideC = (long long)nsplit * n * NB2; y.splitC = (long long)n * NB2;
     y.M = npn; y.N = NB2; y.K = kslice; y.alpha = 1.0; y.beta = 0.0;
+    dbg.begin(st);
     APV_TRY(gemm_f64(y, st));
+    dbg.end(st, 1);
     ++*launches;
     SbW w;
     w.Ypart = Ypart; w.VP = VP; w.Tp = Tp; w.X = X; w.Spart = Spart; w.Z1 = ws.Z1; w.Z2 = ws.Z2;
     w.n = n; w.r = r; w.npn = npn; w.nsplit = nsplit; w.nblk = ceil_div(npn, 64);
+    dbg.begin(st);
     sb_w1_kernel<<<dim3(w.nblk, nz), 256, 0, st>>>(w);
-    sb_w2_kernel<<<dim3(w.nblk, nz), 256, 0, st>>>(w);
+    sb_w2_kernel<<<dim3(w.nblk, nz), 1024, 0, st>>>(w);
+    dbg.end(st, 2);
     *launches += 2;
     GemmArgs u{};                // C22 -= V W^T + W V^T
     u.batch = nz;
@@ -592,7 +761,10 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     u.B = ws.Z2 + (size_t)r * 2 * NB2; u.ldb = 2 * NB2; u.strideB = (long long)n * 2 * NB2;
     u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
     u.M = npn; u.N = npn; u.K = 2 * NB2; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+    u.tri = 1; u.mirror = 1;     // symmetric result: lower tiles computed, stored to both triangles
+    dbg.begin(st);
     APV_TRY(gemm_f64(u, st));
+    dbg.end(st, 3);
     ++*launches;
   }
   APV_CUDA_TRY(cudaEventRecord(ws.ev2[0], st));
@@ -603,12 +775,21 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     ++*launches;
     if (n >= 3) {
       SbChase c;
-      c.AB = AB; c.V2 = ws.Tm; c.prog = prog; c.n = n; c.ldn = ldn; c.nz = nz;
-      // enough warps for the n / (2 NB2) sweeps that can be in flight, at most one CTA per SM
-      const int want = ceil_div(ceil_div(n, NB2) + 2, CHT / 32);
-      const int G = std::max(1, std::min(sms / nz, want));
+      c.AB = AB; c.V2 = ws.Tm; c.gprog = prog; c.n = n; c.ldn = ldn; c.nz = nz; c.dbg = dbg.on ? dclk : nullptr;
+      // groups in flight: a group lasts n / NB2 + 2 CGW time steps and the next one starts 2 CGW + 1 steps later
+      const int ngroups = ceil_div(n - 2, CGW);
+      const int want = ceil_div(n / NB2 + 2 * CGW, 2 * CGW + 1) + 4;
+      const int G = std::max(1, std::min(std::min(sms / nz, want), ngroups));
+      const size_t smem = (size_t)CG_NSLOT * CG_PITCH * sizeof(double);
+      static thread_local bool configured = false;
+      if (!configured) {
+        APV_CUDA_TRY(cudaFuncSetAttribute(sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
       void* args[] = {(void*)&c};
-      APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb2st_chase_kernel, dim3(G * nz), dim3(CHT), args, 0, st));
+      dbg.begin(st);
+      APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb2st_chase_kernel, dim3(G * nz), dim3(CG_THREADS), args, smem, st));
+      dbg.end(st, 4);
       ++*launches;
     }
     sb_extract_tridiag_kernel<<<dim3(ceil_div(n, 256), nz), 256, 0, st>>>(AB, ws.dd, ws.ee, n);
@@ -616,6 +797,21 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   }
   APV_CUDA_TRY(cudaEventRecord(ws.ev2[1], st));
   APV_CUDA_TRY(cudaGetLastError());
+  if (dbg.on) {
+    fprintf(stderr, "two-stage ms: panel QR %.2f | Y = C22 V %.2f | W %.2f | rank-2b update %.2f | chase %.2f\n", dbg.acc[0],
+            dbg.acc[1], dbg.acc[2], dbg.acc[3], dbg.acc[4]);
+    cudaEventDestroy(dbg.e0);
+    cudaEventDestroy(dbg.e1);
+    long long hc[32];
+    cudaMemcpy(hc, dclk, sizeof(hc), cudaMemcpyDeviceToHost);
+    const double us = 1.0 / 1965.0;
+    fprintf(stderr, "  panel QR us (rank 0): load %.0f | block reduce %.0f | deliver %.0f | cluster.sync %.0f | scalars %.0f | row loop %.0f | out %.0f\n",
+            hc[0] * us, hc[1] * us, hc[2] * us, hc[3] * us, hc[4] * us, hc[5] * us, hc[6] * us);
+    fprintf(stderr, "  chase us (CTA 0): compute warp: step %.0f | barrier %.0f ; loader: store+publish %.0f | wait %.0f | load %.0f | barrier %.0f\n",
+            hc[8] * us, hc[11] * us, hc[12] * us, hc[13] * us, hc[14] * us, hc[15] * us);
+    fprintf(stderr, "  chase step us (warp 0): load %.0f | B H %.0f | house %.0f | H' B %.0f | store B %.0f | two-sided %.0f | store D %.0f\n",
+            hc[16] * us, hc[17] * us, hc[18] * us, hc[19] * us, hc[20] * us, hc[21] * us, hc[22] * us);
+  }
   return OK;
 }
 
@@ -633,8 +829,17 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
     APV_CUDA_TRY(cudaFuncSetAttribute(sb2st_apply_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool dbg = getenv("APV_TS_DEBUG") != nullptr;
+  if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   sb2st_apply_q2_kernel<<<dim3(ws.V, ws.nz), Q2T, smem, st>>>(ws.iv, ws.Tm, n, ws.ldn, ws.Vp);
   APV_CUDA_TRY(cudaGetLastError());
+  if (dbg) {
+    float ms = 0.f;
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "two-stage ms: apply Q2 %.2f\n", ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   ++*launches;
   return OK;
 }

@@ -85,6 +85,7 @@ struct GemmArgs {
   int split;
   long long splitA, splitB, splitC;
   int split_ktot;   // > 0: sub-product s covers K indices [s K, min((s + 1) K, split_ktot))
+  int mirror;       // with tri (square C, symmetric result): tiles strictly below the diagonal are also stored transposed
 };
 int gemm_f64(const GemmArgs& g, cudaStream_t st);
 

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_kernel(GemmArgs g
   }
 
   const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  const bool mir = g.tri && g.mirror && m0 >= n0 + BN;
 #pragma unroll
   for (int rt = 0; rt < RT; ++rt) {
     const int r = m0 + wm + rt * 8 + gq;
@@ -146,8 +147,12 @@ __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_kernel(GemmArgs g
         }
         *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
       } else {
-        if (c < g.N) p[0] = v0 + (g.beta != 0.0 ? g.beta * p[0] : 0.0);
-        if (c + 1 < g.N) p[1] = v1 + (g.beta != 0.0 ? g.beta * p[1] : 0.0);
+        if (c < g.N) p[0] = v0 = v0 + (g.beta != 0.0 ? g.beta * p[0] : 0.0);
+        if (c + 1 < g.N) p[1] = v1 = v1 + (g.beta != 0.0 ? g.beta * p[1] : 0.0);
+      }
+      if (mir) {          // 8 lanes (gq) write 8 consecutive doubles of row c: full 32-byte sectors
+        if (c < g.N) C[(size_t)c * g.ldc + r] = v0;
+        if (c + 1 < g.N) C[(size_t)(c + 1) * g.ldc + r] = v1;
       }
     }
   }

@@ -779,6 +779,7 @@ __global__ void __launch_bounds__(BTT) eig_backsolve_kernel(const double* __rest
 // stage, no clusters to repair; used where the matrix fits in one SM (2 n^2 doubles).
 constexpr int JACOBI_MAX_N = 112;
 constexpr int JACOBI_AUTO_N = 48;
+constexpr int TWOSTAGE_AUTO_N = 2048;   // eig_mode 0: two-stage tridiagonalisation (band.cu) from this size on
 
 __global__ void __launch_bounds__(256) eig_jacobi_kernel(const double* __restrict__ Cm, double* __restrict__ lam,
                                                          double* __restrict__ Zt, int* __restrict__ info, int n, int ldn,
@@ -1061,7 +1062,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     if (launches) *launches += nl;
     return OK;
   }
-  const bool two_stage = ws.eig_mode == 3;
+  const bool two_stage = ws.eig_mode == 3 || (ws.eig_mode == 0 && n >= TWOSTAGE_AUTO_N);
   if (two_stage) APV_TRY(twostage_run(ws, st, &nl));
   else APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));

@@ -49,8 +49,12 @@ typedef struct apv_config {
   int32_t perceptual;        /* 0: W == 1 (:326-327); 1: on-device masking model (apv_set_gain_table);
                                 2: weighting spectra supplied by the host per block (apv_set_weights) */
   int32_t normalize_gains;   /* EXPERIMENTAL_NORMALIZE_GAINS (:6,322-324)                           */
-  int32_t eig_mode;          /* 0 auto; 1 tridiagonal + bisection + inverse iteration (top-V);
-                                2 cyclic Jacobi (small n, full spectrum)                            */
+  int32_t eig_mode;          /* 0 auto (2 for n <= 48, 3 for n >= 2048, else 1);
+                                1 one-stage Householder tridiagonalisation + bisection + inverse
+                                  iteration (top-V);
+                                2 cyclic Jacobi (small n, full spectrum);
+                                3 two-stage tridiagonalisation: dense -> band (DMMA, cluster QR)
+                                  -> tridiagonal (bulge chasing), then as 1                         */
   int32_t stats_mode;        /* 0/1 FP64 tensor-core SYRK with implicit Toeplitz operand (default);
                                 2 structured evaluation: first-row correlations + double-double
                                   diagonal recurrence (~J/2 x fewer flops, opt-in)                  */
@@ -179,6 +183,8 @@ int apv_util_gemm(int M, int N, int K, int transA, int transB, double alpha, con
 int apv_util_fft(int n, int inverse, const double* in_ri, double* out_ri);
 /* FP64 DMMA issue-rate microbenchmark: returns achieved TFLOP/s. */
 int apv_bench_dmma_peak(int iters, double* tflops);
+/* CUDA-core FP64 FMA: out3 = {chip TFLOP/s, cycles per dependent DFMA, warp issue interval per sub-partition}. */
+int apv_bench_dfma(int iters, double* out3);
 /* Times nrep launches of the internal GEMM (M=N=K=n) on device data; returns ms per launch. */
 int apv_bench_gemm(int n, int nrep, float* ms);
 
