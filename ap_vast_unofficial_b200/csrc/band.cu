@@ -333,7 +333,7 @@ __global__ void sb_extract_tridiag_kernel(const double* __restrict__ AB, double*
 constexpr int CGW = 3;                        // sweeps per group
 constexpr int CG_NSLOT = 256;                 // window rows (power of two)
 constexpr int CG_PITCH = LDB + 2;             // 66: 16-byte aligned rows, lane stride 67 -> conflict-free block access
-constexpr int CG_THREADS = (CGW + 1) * 32;
+constexpr int CG_THREADS = (2 * CGW + 2) * 32;   // two warps per sweep + storer + fetcher
 static_assert(63 * CGW - 31 + NB2 <= CG_NSLOT, "window too small");   // live rows of a time step + the chunk in flight
 
 __device__ __forceinline__ void bcast_store(double* line, double v, int lane) {
@@ -403,7 +403,6 @@ struct SbChase {
   long long* dbg;      // APV_TS_DEBUG: clock64 totals of CTA 0 (compute step / barrier wait; loader store / wait / load)
 };
 #define CH_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (lane == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
-#define CS_TICK(k) do { if (dbgp && wib == 0) { const long long _t = clock64(); if (lane == 0) a.dbg[16 + k] += _t - ts; ts = _t; } } while (0)
 
 __device__ __forceinline__ int sweep_steps(int n, int s) { return (s <= n - 3) ? 1 + (n - s - 2) / NB2 : 0; }
 
@@ -423,10 +422,16 @@ __device__ __forceinline__ void win_store_diag(double* win, int q0, int lane, co
     if (c <= lane) pd[-c] = D[c];
 }
 
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   extern __shared__ __align__(16) double win[];                  // [CG_NSLOT][CG_PITCH] rows of the band
-  __shared__ __align__(16) double lines[CGW][64];
+  __shared__ __align__(16) double lines[2 * CGW][64];            // per-warp broadcast lines
+  __shared__ __align__(16) double vline[CGW][34];                // new reflector of the step: v[32], tau
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // roles: warps 2w / 2w+1 = off-diagonal-block / diagonal-block half of sweep w's step, then storer and fetcher
+  const int role = wib < 2 * CGW ? (wib & 1) : 2 + (wib - 2 * CGW);
+  const int wsw = wib >> 1;
   const int nz = a.nz, z = blockIdx.x % nz, n = a.n;
   const int cta = blockIdx.x / nz, G = gridDim.x / nz;
   double* AB = a.AB + (size_t)z * n * LDB;
@@ -436,41 +441,45 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   long long* dbgp = nullptr;
   long long tk = clock64();
 
-  // loader: rows [i0, i0 + 32) of the band -> window (zero rows beyond the matrix) once the previous group is past them
+  // fetcher: rows [i0, i0 + 32) of the band -> window (zero rows beyond the matrix) once the previous group is past them
   auto load_chunk = [&](int g, int i0) {
     if (g > 0 && i0 < n) {
       const int need = min(n, i0 + NB2);
       if (lane == 0) {
-        // relaxed polling with back-off (an acquire load per iteration invalidates L1 every time and slows the
-        // compute warps' shared-memory traffic), one acquire fence when the bound is reached
+        // relaxed polling with back-off, one acquire fence when the bound is reached
         int v;
         for (;;) {
           asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gprog + (g - 1)) : "memory");
           if (v >= need) break;
-          __nanosleep(64);
+          __nanosleep(32);
         }
         __threadfence();
       }
       __syncwarp();
     }
     CH_TICK(1);
-    double2 buf[8];
-    for (int r8 = 0; r8 < NB2; r8 += 8) {
+    double2 buf[NB2];                   // all 32 rows in flight at once: one L2 round trip per chunk
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + r8 + u;
-        buf[u] = (i < n) ? __ldcg(reinterpret_cast<const double2*>(AB + (size_t)i * LDB) + lane) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) reinterpret_cast<double2*>(win_row(win, i0 + r8 + u))[lane] = buf[u];
+    for (int u = 0; u < NB2; ++u) {
+      const int i = i0 + u;
+      buf[u] = (i < n) ? __ldcg(reinterpret_cast<const double2*>(AB + (size_t)i * LDB) + lane) : make_double2(0.0, 0.0);
     }
+#pragma unroll
+    for (int u = 0; u < NB2; ++u) reinterpret_cast<double2*>(win_row(win, i0 + u))[lane] = buf[u];
     CH_TICK(2);
   };
-  // loader: window rows [y0, y1) -> global, then publish the bound
+  // storer: window rows [y0, y1) -> global, then publish the bound
   auto store_rows = [&](int g, int y0, int y1, int publish) {
-    for (int i = y0; i < y1; ++i)
-      reinterpret_cast<double2*>(AB + (size_t)i * LDB)[lane] = reinterpret_cast<const double2*>(win_row(win, i))[lane];
-    __threadfence();
+    for (int i = y0; i < y1; i += 8) {
+      double2 buf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i + u < y1) buf[u] = reinterpret_cast<const double2*>(win_row(win, i + u))[lane];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i + u < y1) reinterpret_cast<double2*>(AB + (size_t)(i + u) * LDB)[lane] = buf[u];
+    }
+    // the warp barrier orders the lanes' stores before lane 0's release (release is cumulative)
     __syncwarp();
     if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gprog + g), "r"(publish) : "memory");
     CH_TICK(0);
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
 
   for (int g = cta; g < ngroups; g += G) {
     // debug clocks: the first group only (it never waits for a predecessor: the unthrottled pace of one time step)
-    dbgp = (a.dbg && blockIdx.x == 0 && g == 0 && (wib == 0 || wib == CGW)) ? a.dbg + 8 + (wib == CGW ? 4 : 0) : nullptr;
+    dbgp = (a.dbg && blockIdx.x == 0 && g == 0 && (wib == 0 || role >= 2)) ? a.dbg + 8 + (role >= 2 ? 4 * (role - 1) : 0) : nullptr;
     tk = clock64();
     const int s0 = g * CGW;
     const int nst0 = sweep_steps(n, s0);
@@ -488,90 +497,89 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
       const int ns = sweep_steps(n, s0 + w);
       if (ns > 0) T = max(T, ns + 2 * w);
     }
-    if (wib == CGW) load_chunk(g, s0 + 1);
+    if (role == 3) load_chunk(g, s0 + 1);
     __syncthreads();
-    // compute-warp state carried from step to step
-    const int s = s0 + wib;
-    const int nst = (wib < CGW) ? sweep_steps(n, s) : 0;
-    double v = 0.0, tau = 0.0, beta = 0.0;
-    int ystored = s0 + 1;                       // loader: rows below are back in global memory
+    const int s = s0 + wsw;
+    const int nst = (role < 2) ? sweep_steps(n, s) : 0;
+    double v = 0.0, tau = 0.0, beta = 0.0;      // role 0: reflector carried from step to step
+    int ystored = s0 + 1;                       // storer: rows below are back in global memory
     for (int t = 0; t < T; ++t) {
-      if (wib < CGW) {
-        const int k = t - 2 * wib;
-        if (k == 0 && nst > 0) {
-          // ---- step 0: reflector of column s, two-sided update of the first diagonal block
-          const int r0 = s + 1;
-          double D[32];
-          win_load_diag(win, r0, lane, D);
-          double* myrow = win_row(win, r0 + lane);
-          const double x = myrow[1 + lane];              // A[s+1+lane][s]
-          warp_house(x, lane, v, tau, beta);
-          if (lane == 0) myrow[1] = beta;
-          two_sided32(D, v, tau, lane, lines[wib]);
-          win_store_diag(win, r0, lane, D);
-          if (r0 + lane < n) V2[(size_t)s * a.ldn + r0 + lane] = (lane == 0) ? tau : v;
-        } else if (k > 0 && k < nst) {
-          const int q0 = s + 1 + k * NB2;
+      if (role < 2) {
+        const int k = t - 2 * wsw;
+        if (k >= 0 && k < nst) {
+          const int q0 = s + 1 + k * NB2;       // rows of the step (k = 0: the first diagonal block)
           double* line = lines[wib];
-          double B[32], D[32];
-          long long ts = clock64();
-          double* pb = win_row(win, q0 + lane) + NB2 + lane;      // B(lane, c) = pb[-c]
+          if (role == 0) {
+            double* myrow = win_row(win, q0 + lane);
+            if (k == 0) {
+              // reflector of column s
+              warp_house(myrow[1 + lane], lane, v, tau, beta);          // A[s+1+lane][s]
+              vline[wsw][lane] = v;
+              if (lane == 0) { vline[wsw][32] = tau; myrow[1] = beta; }
+              pair_sync(1 + wsw);
+            } else {
+              double B[32];
+              double* pb = myrow + NB2 + lane;                        // B(lane, c) = pb[-c]
 #pragma unroll
-          for (int c = 0; c < 32; ++c) B[c] = pb[-c];
-          win_load_diag(win, q0, lane, D);
-          // B <- B H_prev
-          bcast_store(line, v, lane);
-          CS_TICK(0);
-          double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+              for (int c = 0; c < 32; ++c) B[c] = pb[-c];
+              // B <- B H_prev
+              bcast_store(line, v, lane);
+              double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const double2 va = *reinterpret_cast<const double2*>(line + c);
-            const double2 vb = *reinterpret_cast<const double2*>(line + c + 2);
-            y0 = fma(B[c], va.x, y0);
-            y1 = fma(B[c + 1], va.y, y1);
-            y2 = fma(B[c + 2], vb.x, y2);
-            y3 = fma(B[c + 3], vb.y, y3);
-          }
-          const double y = tau * ((y0 + y1) + (y2 + y3));
+              for (int c = 0; c < 32; c += 4) {
+                const double2 va = *reinterpret_cast<const double2*>(line + c);
+                const double2 vb = *reinterpret_cast<const double2*>(line + c + 2);
+                y0 = fma(B[c], va.x, y0);
+                y1 = fma(B[c + 1], va.y, y1);
+                y2 = fma(B[c + 2], vb.x, y2);
+                y3 = fma(B[c + 3], vb.y, y3);
+              }
+              const double y = tau * ((y0 + y1) + (y2 + y3));
+              // the first column decides the new reflector: finish it first and hand it to the diagonal-block warp
+              B[0] = fma(-y, line[0], B[0]);
+              double vn, taun;
+              warp_house(B[0], lane, vn, taun, beta);
+              vline[wsw][lane] = vn;
+              if (lane == 0) vline[wsw][32] = taun;
+              pair_sync(1 + wsw);
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const double2 vv = *reinterpret_cast<const double2*>(line + c);
-            B[c] = fma(-y, vv.x, B[c]);
-            B[c + 1] = fma(-y, vv.y, B[c + 1]);
-          }
-          CS_TICK(1);
-          // new reflector from the first column of B
-          warp_house(B[0], lane, v, tau, beta);
-          B[0] = (lane == 0) ? beta : 0.0;
-          CS_TICK(2);
-          // B[:, 1:] <- H' B[:, 1:]
-          {
-            double vals[32];
+              for (int c = 2; c < 32; c += 2) {
+                const double2 vv = *reinterpret_cast<const double2*>(line + c);
+                B[c] = fma(-y, vv.x, B[c]);
+                B[c + 1] = fma(-y, vv.y, B[c + 1]);
+              }
+              B[1] = fma(-y, line[1], B[1]);
+              v = vn; tau = taun;
+              B[0] = (lane == 0) ? beta : 0.0;
+              // B[:, 1:] <- H' B[:, 1:]
+              double vals[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) vals[c] = v * B[c];
-            const double u = tau * colsum32(vals, lane);       // lane c: tau v^T B[:, c]
-            bcast_store(line, u, lane);
+              for (int c = 0; c < 32; ++c) vals[c] = v * B[c];
+              const double u = tau * colsum32(vals, lane);       // lane c: tau v^T B[:, c]
+              bcast_store(line, u, lane);
 #pragma unroll
-            for (int c = 2; c < 32; c += 2) {
-              const double2 uu = *reinterpret_cast<const double2*>(line + c);
-              B[c] = fma(-v, uu.x, B[c]);
-              B[c + 1] = fma(-v, uu.y, B[c + 1]);
+              for (int c = 2; c < 32; c += 2) {
+                const double2 uu = *reinterpret_cast<const double2*>(line + c);
+                B[c] = fma(-v, uu.x, B[c]);
+                B[c + 1] = fma(-v, uu.y, B[c + 1]);
+              }
+              B[1] = fma(-v, line[1], B[1]);
+#pragma unroll
+              for (int c = 0; c < 32; ++c) pb[-c] = B[c];
             }
-            B[1] = fma(-v, line[1], B[1]);
+            if (q0 + lane < n) V2[(size_t)s * a.ldn + q0 + lane] = (lane == 0) ? tau : v;
+          } else {
+            // diagonal block: D <- H' D H'
+            double D[32];
+            win_load_diag(win, q0, lane, D);
+            pair_sync(1 + wsw);
+            two_sided32(D, vline[wsw][lane], vline[wsw][32], lane, line);
+            win_store_diag(win, q0, lane, D);
           }
-          CS_TICK(3);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) pb[-c] = B[c];
-          CS_TICK(4);
-          two_sided32(D, v, tau, lane, line);
-          CS_TICK(5);
-          win_store_diag(win, q0, lane, D);
-          CS_TICK(6);
-          if (q0 + lane < n) V2[(size_t)s * a.ldn + q0 + lane] = (lane == 0) ? tau : v;
         }
         CH_TICK(0);
-      } else {
-        // ---- loader warp: write back what time step t - 1 finished, fetch what time step t + 1 needs
+      } else if (role == 2) {
+        // ---- storer: write back what time step t - 1 finished and publish the group's row bound
         if (t > 0) {
           int ynew = n, remaining = 0;
 #pragma unroll
@@ -588,12 +596,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
             ystored = ynew;
           }
         }
+      } else {
+        // ---- fetcher: the rows the leading sweep needs in time step t + 1
         if (t + 1 <= nst0) load_chunk(g, s0 + 1 + (t + 1) * NB2);
       }
       __syncthreads();
       CH_TICK(3);
     }
-    if (wib == CGW) store_rows(g, ystored, min(n, s0 + 1 + (nst0 + 1) * NB2), PROG_DONE);
+    if (role == 2) store_rows(g, ystored, min(n, s0 + 1 + (nst0 + 1) * NB2), PROG_DONE);
     __syncthreads();
   }
 }
@@ -701,7 +711,11 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   APV_CUDA_TRY(cudaMemsetAsync(prog, 0, (size_t)nz * n * sizeof(int), st));
 
   // ---- stage 1
-  for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) {
+  // Look-ahead: as soon as panel k's W is known, the NB2 columns of the next panel are updated on their own
+  // (a skinny GEMM), the next panel's QR (latency-bound, one cluster per zone) starts on a high-priority side
+  // stream, and the bulk of the rank-2b update (all the other SMs) runs beside it on the main stream.
+  const bool lookahead = !dbg.on && ws.st2 != nullptr && !getenv("APV_TS_NO_LOOKAHEAD");
+  auto launch_qr = [&](int j0, cudaStream_t qs) -> int {
     const int r = j0 + NB2, npn = n - r;
     // cluster size: smallest of 1, 2, 4, 8, 16 whose slab fits in shared memory
     const int max_rows = (184 * 1024) / (PP * (int)sizeof(double));
@@ -724,15 +738,21 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       configured = std::max(smem, (size_t)(184 * 1024));
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CS, nz); cfg.blockDim = dim3(QRT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(CS, nz); cfg.blockDim = dim3(QRT); cfg.dynamicSmemBytes = smem; cfg.stream = qs;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    dbg.begin(st);
+    dbg.begin(qs);
     APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel, p));
-    dbg.end(st, 0);
+    dbg.end(qs, 0);
     ++*launches;
+    return OK;
+  };
+  bool qr_done = false;          // the QR of the current panel was issued by the previous iteration (look-ahead)
+  for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) {
+    const int r = j0 + NB2, npn = n - r;
+    if (!qr_done) APV_TRY(launch_qr(j0, st));
     // Y = C22 V in K slices
     int nsplit = std::max(1, std::min(nsm, (2 * sms) / std::max(1, nz * ceil_div(npn, 128))));
     const int kslice = round_up(ceil_div(npn, nsplit), 16);
@@ -755,17 +775,38 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     sb_w2_kernel<<<dim3(w.nblk, nz), 1024, 0, st>>>(w);
     dbg.end(st, 2);
     *launches += 2;
-    GemmArgs u{};                // C22 -= V W^T + W V^T
+    // C22 -= V W^T + W V^T
+    GemmArgs u{};
     u.batch = nz;
     u.A = ws.Z1 + (size_t)r * 2 * NB2; u.lda = 2 * NB2; u.strideA = (long long)n * 2 * NB2;
     u.B = ws.Z2 + (size_t)r * 2 * NB2; u.ldb = 2 * NB2; u.strideB = (long long)n * 2 * NB2;
     u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
-    u.M = npn; u.N = npn; u.K = 2 * NB2; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
-    u.tri = 1; u.mirror = 1;     // symmetric result: lower tiles computed, stored to both triangles
-    dbg.begin(st);
-    APV_TRY(gemm_f64(u, st));
-    dbg.end(st, 3);
-    ++*launches;
+    u.K = 2 * NB2; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+    const bool next_panel = n - r - NB2 >= 2;
+    qr_done = false;
+    if (lookahead && next_panel) {
+      GemmArgs c = u;            // the next panel's columns (its diagonal block and sub-diagonal panel)
+      c.M = npn; c.N = NB2;
+      APV_TRY(gemm_f64(c, st));
+      APV_CUDA_TRY(cudaEventRecord(ws.ev2[2], st));
+      APV_CUDA_TRY(cudaStreamWaitEvent(ws.st2, ws.ev2[2], 0));
+      APV_TRY(launch_qr(r, ws.st2));
+      APV_CUDA_TRY(cudaEventRecord(ws.ev2[3], ws.st2));
+      qr_done = true;
+      u.A += (size_t)NB2 * 2 * NB2; u.B += (size_t)NB2 * 2 * NB2; u.C += (size_t)NB2 * ldn + NB2;
+      u.M = npn - NB2; u.N = npn - NB2;
+      u.tri = 1; u.mirror = 1;   // symmetric result: lower tiles computed, stored to both triangles
+      APV_TRY(gemm_f64(u, st));
+      APV_CUDA_TRY(cudaStreamWaitEvent(st, ws.ev2[3], 0));
+      *launches += 2;
+    } else {
+      u.M = npn; u.N = npn;
+      u.tri = 1; u.mirror = 1;
+      dbg.begin(st);
+      APV_TRY(gemm_f64(u, st));
+      dbg.end(st, 3);
+      ++*launches;
+    }
   }
   APV_CUDA_TRY(cudaEventRecord(ws.ev2[0], st));
   // ---- stage 2
@@ -807,10 +848,8 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     const double us = 1.0 / 1965.0;
     fprintf(stderr, "  panel QR us (rank 0): load %.0f | block reduce %.0f | deliver %.0f | cluster.sync %.0f | scalars %.0f | row loop %.0f | out %.0f\n",
             hc[0] * us, hc[1] * us, hc[2] * us, hc[3] * us, hc[4] * us, hc[5] * us, hc[6] * us);
-    fprintf(stderr, "  chase us (CTA 0): compute warp: step %.0f | barrier %.0f ; loader: store+publish %.0f | wait %.0f | load %.0f | barrier %.0f\n",
-            hc[8] * us, hc[11] * us, hc[12] * us, hc[13] * us, hc[14] * us, hc[15] * us);
-    fprintf(stderr, "  chase step us (warp 0): load %.0f | B H %.0f | house %.0f | H' B %.0f | store B %.0f | two-sided %.0f | store D %.0f\n",
-            hc[16] * us, hc[17] * us, hc[18] * us, hc[19] * us, hc[20] * us, hc[21] * us, hc[22] * us);
+    fprintf(stderr, "  chase us (first group): B-warp step %.0f | barrier %.0f ; storer: store+publish %.0f | barrier %.0f ; fetcher: wait %.0f | load %.0f | barrier %.0f\n",
+            hc[8] * us, hc[11] * us, hc[12] * us, hc[15] * us, hc[17] * us, hc[18] * us, hc[19] * us);
   }
   return OK;
 }

@@ -40,7 +40,8 @@ struct JdiagWs {
   double* Zt = nullptr;     // [nz][V][n] eigenvectors of T -> of C -> joint eigenvectors U (row v)
   int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
   double* ts2 = nullptr;    // two-stage tridiagonalisation scratch (band.cu): V panel, Y slices, X, S partials, T, band, flags
-  cudaEvent_t ev2[2] = {};  // two-stage: end of stage 1 (dense -> band), end of stage 2 (band -> tridiagonal)
+  cudaEvent_t ev2[4] = {};  // two-stage: end of stage 1 (dense -> band), end of stage 2 (band -> tridiagonal), look-ahead fork / join
+  cudaStream_t st2 = nullptr;   // high-priority side stream of the look-ahead panel factorisation
   int Vp = 0;
   size_t bytes = 0;
   cudaEvent_t ev[8] = {};   // phase boundaries: prep | chol | reduce | tridiag | eig | backtransform | solve

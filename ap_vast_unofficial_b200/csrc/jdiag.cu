@@ -906,7 +906,12 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.info, (size_t)nz * 4 * sizeof(int)));
   APV_TRY(al((void**)&ws.ts2, twostage_scratch_bytes(n, nz, twostage_nsplit_max())));
   for (auto& e : ws.ev) APV_CUDA_TRY(cudaEventCreate(&e));
-  for (auto& e : ws.ev2) APV_CUDA_TRY(cudaEventCreate(&e));
+  for (auto& e : ws.ev2) APV_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDefault));
+  {
+    int lo = 0, hi = 0;
+    APV_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    APV_CUDA_TRY(cudaStreamCreateWithPriority(&ws.st2, cudaStreamNonBlocking, hi));
+  }
   ws.npanel = ceil_div(n, NBT);
   ws.pev = new cudaEvent_t[2 * ws.npanel]();
   for (int i = 0; i < 2 * ws.npanel; ++i) APV_CUDA_TRY(cudaEventCreate(&ws.pev[i]));
@@ -923,6 +928,7 @@ void jdiag_free(JdiagWs& ws) {
     if (e) cudaEventDestroy(e);
   for (auto& e : ws.ev2)
     if (e) cudaEventDestroy(e);
+  if (ws.st2) cudaStreamDestroy(ws.st2);
   if (ws.pev) {
     for (int i = 0; i < 2 * ws.npanel; ++i)
       if (ws.pev[i]) cudaEventDestroy(ws.pev[i]);
