@@ -722,6 +722,8 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     int CS = 1;
     while (CS < QR_MAXCS && ceil_div(npn, CS) > max_rows) CS *= 2;
     if (npn > 64) CS = std::max(CS, 8);                       // spread the rows anyway: the column loop is latency-bound
+    static const int cs16_from = getenv("APV_QR_CS16") ? atoi(getenv("APV_QR_CS16")) : 1 << 30;
+    if (npn >= cs16_from) CS = 16;
     if (ceil_div(npn, CS) > max_rows) {
       snprintf(g_err, sizeof(g_err), "two-stage tridiagonalisation: n = %d exceeds the panel capacity", n);
       return EINVAL_;
@@ -782,6 +784,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     u.B = ws.Z2 + (size_t)r * 2 * NB2; u.ldb = 2 * NB2; u.strideB = (long long)n * 2 * NB2;
     u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
     u.K = 2 * NB2; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+    u.bn = 64;                   // K = 64: two CTAs per SM hide the tile load / read-modify-write latency
     const bool next_panel = n - r - NB2 >= 2;
     qr_done = false;
     if (lookahead && next_panel) {

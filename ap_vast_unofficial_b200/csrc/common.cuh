@@ -86,6 +86,7 @@ struct GemmArgs {
   long long splitA, splitB, splitC;
   int split_ktot;   // > 0: sub-product s covers K indices [s K, min((s + 1) K, split_ktot))
   int mirror;       // with tri (square C, symmetric result): tiles strictly below the diagonal are also stored transposed
+  int bn;           // 0: tile width by N (32 / 64 / 128); 64: force the 128 x 64 tile (two CTAs per SM: short-K updates)
 };
 int gemm_f64(const GemmArgs& g, cudaStream_t st);
 

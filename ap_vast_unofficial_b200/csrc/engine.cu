@@ -515,14 +515,20 @@ int apv_kernel_times(apv_handle* h, float* ms4) {
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   if (h->nz > 0) {
     cudaEventElapsedTime(&ms4[1], h->ev_syrk[0], h->ev_syrk[1]);
-    float tot = 0.f;
-    for (int p = 0; p < h->jd.npanel; ++p) {
-      float t = 0.f;
-      cudaEventElapsedTime(&t, h->jd.pev[2 * p], h->jd.pev[2 * p + 1]);
-      tot += t;
+    if (h->jd.last_two_stage) {          // band reduction | bulge chasing of the last block
+      cudaEventElapsedTime(&ms4[0], h->jd.ev[2], h->jd.ev2[0]);
+      cudaEventElapsedTime(&ms4[3], h->jd.ev2[0], h->jd.ev2[1]);
+      ms4[2] = -1.f;
+    } else if (h->jd.last_panels) {
+      float tot = 0.f;
+      for (int p = 0; p < h->jd.npanel; ++p) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->jd.pev[2 * p], h->jd.pev[2 * p + 1]);
+        tot += t;
+      }
+      ms4[0] = tot;
+      ms4[2] = (float)h->jd.npanel;
     }
-    ms4[0] = tot;
-    ms4[2] = (float)h->jd.npanel;
   }
   return OK;
 }

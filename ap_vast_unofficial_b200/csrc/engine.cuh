@@ -47,6 +47,8 @@ struct JdiagWs {
   cudaEvent_t ev[8] = {};   // phase boundaries: prep | chol | reduce | tridiag | eig | backtransform | solve
   cudaEvent_t* pev = nullptr;   // [2 * npanel] events around every td_panel_kernel launch (roofline timing)
   int npanel = 0;
+  bool last_two_stage = false;  // the last jdiag_run used the two-stage tridiagonalisation (band.cu)
+  bool last_panels = false;     // ... the one-stage panel kernels (pev recorded)
 };
 int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode);
 void jdiag_free(JdiagWs& ws);

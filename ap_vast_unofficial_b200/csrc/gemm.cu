@@ -9,6 +9,8 @@
 // double buffering of the global->shared copies, padded shared tiles so every fragment load is bank-conflict
 // free (row pitch == 4 mod 16 doubles).  blockIdx.z = batch * split + s: `split` independent K-slices or
 // sub-problems inside one batch entry advance the operands by splitA/B/C elements.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace apv {
@@ -175,7 +177,9 @@ int launch_bn(const GemmArgs& g, cudaStream_t st) {
 template <int TA, int TB>
 int launch(const GemmArgs& g, cudaStream_t st) {
   if (g.N <= 32) return launch_bn<TA, TB, 32>(g, st);
-  if (g.N <= 64) return launch_bn<TA, TB, 64>(g, st);
+  // 128 x 64 tiles run two CTAs per SM: better for every product of this engine with K <= ~1000 (the delayed
+  // rank-64 .. rank-256 updates are latency-bound per tile); the 128 x 128 tile is kept for long-K products
+  if (g.N <= 64 || g.bn == 64 || (g.bn == 0 && g.K <= 1024)) return launch_bn<TA, TB, 64>(g, st);
   return launch_bn<TA, TB, 128>(g, st);
 }
 

@@ -42,93 +42,175 @@ __global__ void prep_kernel(Ptr2 bright, Ptr2 dark, int ld_in, double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky of one diagonal block (<= NB x NB) and the inverse of its factor.  grid (nz), 256 threads.
-// The lower triangle lives in registers: thread t owns row r = t/4 and the columns c = (t%4) + 4q <= r.
-// Right-looking elimination with two barriers per column (pivot; scaled column), then the inverse by the same
-// elimination applied to the identity (L X = I, one row of X final per step).
-__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ Lm, double* __restrict__ Dinv, int n,
+// Cholesky of one diagonal block (<= NB x NB, NB = 64) and the inverse of its factor.  grid (nz), 128 threads.
+// The block is split 2 x 2 into 32 x 32 tiles; every tile operation is warp-synchronous with lane = row and the
+// row in registers, so the only CTA barriers are the eight phase boundaries (the first version eliminated column
+// by column with two CTA barriers per column: 94 us per block; this one 10 us):
+//   L11 = chol(A11) | L21 = A21 L11^-T, X11 = L11^-1 | A22 -= L21 L21^T | L22 = chol(A22) |
+//   X22 = L22^-1, T = L21 X11 | X21 = -X22 T.
+// A non-positive (or NaN) pivot records its 1-based global index in info[z][0] (first one wins) and is replaced
+// by 1 so the launch sequence can finish; the host raises LinAlgError (numpy.linalg.cholesky, apvast.py:22-24).
+constexpr int CDP = NB + 1;      // shared-memory pitch
+
+// lane = row of a 32 x 32 symmetric tile held in a[] (entries c <= lane); on exit a[] holds the row of its Cholesky
+// factor.  col: 32 doubles of scratch; invd: reciprocals of the diagonal; returns the first bad pivot or -1.
+__device__ __forceinline__ int warp_chol32(double (&a)[32], int lane, double* col, double* invd) {
+  int bad = -1;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0)) {                       // also catches NaN
+      if (bad < 0) bad = j;
+      d = 1.0;
+    }
+    const double inv = rsqrt(d);
+    const double l = (lane == j) ? d * inv : a[j] * inv;
+    a[j] = (lane >= j) ? l : 0.0;
+    __syncwarp();
+    col[lane] = a[j];
+    if (lane == j) invd[j] = inv;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) a[c] = fma(-a[j], col[c], a[c]);   // (entries c > lane are never used)
+  }
+  return bad;
+}
+
+__global__ void __launch_bounds__(128) chol_diag_kernel(double* __restrict__ Lm, double* __restrict__ Dinv, int n,
                                                         int ldn, int k0, int nbk, int nblk, int* __restrict__ info) {
-  __shared__ double Ls[NB][NB + 1];
-  __shared__ double colj[NB];
-  __shared__ double xrow[NB];
-  const int z = blockIdx.x, tid = threadIdx.x;
-  const int r = tid >> 2, cg = tid & 3;
+  extern __shared__ double cd_sm[];
+  double (*S)[CDP] = reinterpret_cast<double (*)[CDP]>(cd_sm);               // A -> L (lower)
+  double (*X)[CDP] = reinterpret_cast<double (*)[CDP]>(cd_sm + NB * CDP);    // L^-1 (lower)
+  __shared__ double Tm_[32][33];         // L21 X11
+  __shared__ double invd[NB];
+  __shared__ double cols[2][32];
+  const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* A = Lm + (size_t)z * n * ldn + (size_t)k0 * ldn + k0;
-  double a[NB / 4];
-#pragma unroll
-  for (int q = 0; q < NB / 4; ++q) {
-    const int c = cg + 4 * q;
-    a[q] = (c <= r) ? ((r < nbk && c < nbk) ? A[(size_t)r * ldn + c] : (r == c ? 1.0 : 0.0)) : 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (r == j && cg == (j & 3)) {
-      double d = a[j >> 2];
-      if (!(d > 0.0)) {                       // also catches NaN
-        if (j < nbk && info[z * 4] == 0) info[z * 4] = k0 + j + 1;
-        d = 1.0;
-      }
-      d = sqrt(d);
-      a[j >> 2] = d;
-      colj[j] = d;
-    }
-    __syncthreads();
-    if (cg == (j & 3) && r > j) {
-      const double l = a[j >> 2] / colj[j];
-      a[j >> 2] = l;
-      colj[r] = l;
-    }
-    __syncthreads();
-    if (r > j) {
-      const double lr = colj[r];
-#pragma unroll
-      for (int q = 0; q < NB / 4; ++q) {
-        const int c = cg + 4 * q;
-        if (c > j && c <= r) a[q] = fma(-lr, colj[c], a[q]);
-      }
-    }
-  }
-  // factor -> shared + global (zeros above the diagonal)
-#pragma unroll
-  for (int q = 0; q < NB / 4; ++q) {
-    const int c = cg + 4 * q;
-    Ls[r][c] = (c <= r) ? a[q] : 0.0;
-    if (r < nbk && c < nbk) A[(size_t)r * ldn + c] = (c <= r) ? a[q] : 0.0;
+  for (int i = tid; i < NB * NB; i += 128) {
+    const int r = i / NB, c = i % NB;
+    S[r][c] = (c <= r) ? ((r < nbk && c < nbk) ? A[(size_t)r * ldn + c] : (r == c ? 1.0 : 0.0)) : 0.0;
+    X[r][c] = 0.0;
   }
   __syncthreads();
-  // inverse: x holds the running right-hand side rows of L X = I
-  double x[NB / 4];
+  double a[32];
+  // ---- L11
+  if (warp == 0) {
 #pragma unroll
-  for (int q = 0; q < NB / 4; ++q) x[q] = (cg + 4 * q == r) ? 1.0 : 0.0;
+    for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
+    const int bad = warp_chol32(a, lane, cols[0], invd);
+    if (bad >= 0 && bad < nbk && lane == 0 && info[z * 4] == 0) info[z * 4] = k0 + bad + 1;
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (r == j) {
-      const double inv = 1.0 / Ls[j][j];
-#pragma unroll
-      for (int q = 0; q < NB / 4; ++q) {
-        const int c = cg + 4 * q;
-        if (c <= j) {
-          x[q] *= inv;
-          xrow[c] = x[q];
-        }
-      }
-    }
-    __syncthreads();
-    if (r > j) {
-      const double lrj = Ls[r][j];
-#pragma unroll
-      for (int q = 0; q < NB / 4; ++q) {
-        const int c = cg + 4 * q;
-        if (c <= j) x[q] = fma(-lrj, xrow[c], x[q]);
-      }
-    }
-    __syncthreads();
+    for (int c = 0; c < 32; ++c) S[lane][c] = (c <= lane) ? a[c] : 0.0;
   }
-  double* Di = Dinv + ((size_t)z * nblk + k0 / NB) * NB * NB;
+  __syncthreads();
+  // ---- L21 = A21 L11^-T (warp 1, lane = row of A21);  X11 = L11^-1 (warp 2, lane = column of X11)
+  if (warp == 1) {
 #pragma unroll
-  for (int q = 0; q < NB / 4; ++q) {
-    const int c = cg + 4 * q;
-    Di[r * NB + c] = (c <= r && r < nbk && c < nbk) ? x[q] : 0.0;
+    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][c];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      double t = a[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t = fma(-a[k], S[j][k], t);
+      a[j] = t * invd[j];
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) S[32 + lane][c] = a[c];
+  } else if (warp == 2) {
+    // column `lane` of X11: x_r = (delta_{r,lane} - sum_{k<r} L[r][k] x_k) / L[r][r], zero above the diagonal
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double t = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) t = fma(-S[r][k], a[k], t);
+      a[r] = (r >= lane) ? t * invd[r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) X[r][lane] = a[r];
+  }
+  __syncthreads();
+  // ---- A22 -= L21 L21^T: lane = row, every warp eight columns
+  {
+    double l[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int c = warp * 8 + cc;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        t0 = fma(l[k], S[32 + c][k], t0);
+        t1 = fma(l[k + 1], S[32 + c][k + 1], t1);
+      }
+      if (c <= lane) S[32 + lane][32 + c] -= t0 + t1;
+    }
+  }
+  __syncthreads();
+  // ---- L22
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
+    const int bad = warp_chol32(a, lane, cols[0], invd + 32);
+    if (bad >= 0 && 32 + bad < nbk && lane == 0 && info[z * 4] == 0) info[z * 4] = k0 + 32 + bad + 1;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) S[32 + lane][32 + c] = (c <= lane) ? a[c] : 0.0;
+  } else if (warp == 1 || warp == 3) {
+    // T = L21 X11, lane = row, 16 columns per warp:  T[r][c] = sum_{k >= c} L21[r][k] X11[k][c]
+    double l[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
+    const int c0 = (warp == 1) ? 0 : 16;
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const int c = c0 + cc;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        t0 = fma(l[k], X[k][c], t0);
+        t1 = fma(l[k + 1], X[k + 1][c], t1);
+      }
+      Tm_[lane][c] = t0 + t1;
+    }
+  }
+  __syncthreads();
+  // ---- X22 = L22^-1 (warp 2)
+  if (warp == 2) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double t = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) t = fma(-S[32 + r][32 + k], a[k], t);
+      a[r] = (r >= lane) ? t * invd[32 + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) X[32 + r][32 + lane] = a[r];
+  }
+  __syncthreads();
+  // ---- X21 = -X22 T: lane = row, eight columns per warp
+  {
+    double xr[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) xr[k] = X[32 + lane][32 + k];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int c = warp * 8 + cc;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        t0 = fma(xr[k], Tm_[k][c], t0);
+        t1 = fma(xr[k + 1], Tm_[k + 1][c], t1);
+      }
+      X[32 + lane][c] = -(t0 + t1);
+    }
+  }
+  __syncthreads();
+  double* Di = Dinv + ((size_t)z * nblk + k0 / NB) * NB * NB;
+  for (int i = tid; i < NB * NB; i += 128) {
+    const int r = i / NB, c = i % NB;
+    const bool in = c <= r && r < nbk && c < nbk;
+    if (r < nbk && c < nbk) A[(size_t)r * ldn + c] = (c <= r) ? S[r][c] : 0.0;
+    Di[i] = in ? X[r][c] : 0.0;
   }
 }
 
@@ -998,12 +1080,13 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
 
   // ---- blocked Cholesky of Lm (lower)
   const int nblk = ceil_div(n, NB);
-  const size_t chol_smem = 0;
+  const size_t chol_smem = (size_t)2 * NB * CDP * sizeof(double);
+  APV_TRY(ensure_smem(chol_diag_kernel, chol_smem));
   for (int s0 = 0; s0 < n; s0 += SB) {
     const int s1 = std::min(n, s0 + SB);
     for (int k0 = s0; k0 < s1; k0 += NB) {
       const int nbk = std::min(NB, n - k0);
-      chol_diag_kernel<<<nz, 256, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
+      chol_diag_kernel<<<nz, 128, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
       ++nl;
       const int below = n - k0 - nbk;
       if (below > 0) {
@@ -1054,6 +1137,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   // ---- blocked Householder tridiagonalisation of Cm
   const bool use_jacobi = (ws.eig_mode == 2 && n <= JACOBI_MAX_N) || (ws.eig_mode == 0 && n <= JACOBI_AUTO_N);
   if (use_jacobi) {
+    ws.last_two_stage = ws.last_panels = false;
     const int np = (n + 1) & ~1;
     const size_t jsm = (size_t)2 * np * np * sizeof(double);
     APV_TRY(ensure_smem(eig_jacobi_kernel, jsm));
@@ -1069,6 +1153,8 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     return OK;
   }
   const bool two_stage = ws.eig_mode == 3 || (ws.eig_mode == 0 && n >= TWOSTAGE_AUTO_N);
+  ws.last_two_stage = two_stage;
+  ws.last_panels = !two_stage;
   if (two_stage) APV_TRY(twostage_run(ws, st, &nl));
   else APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));

@@ -14,9 +14,11 @@ Printed JSON line (rank 0):
             events on the engine's stream, max over ranks)
   e2e       the same metric through the public drop-in call ``apvast.process_input_buffers`` with HOST
             buffers: pinned H2D of the hop and D2H of the rendered outputs inside the timed region
-  roofline  the dominant kernel (td_panel_kernel: Householder tridiagonalisation, HBM/L2 bound):
-            algorithmic bytes per block / sum of its launch durations, against MEASURED_PEAKS.json hbm_gbs
-  roofline_stats   the FP64 tensor-core statistics SYRK against the DMMA peak measured live
+  roofline  the dominant kernel.  At cfg3 (n >= 2048: two-stage tridiagonalisation) that is the FP64 tensor-core
+            statistics SYRK: algorithmic flops per block / its launch duration against the DMMA peak measured
+            live in this process (MEASURED_PEAKS.json has no FP64 figure).  At cfg2 (one-stage tridiagonalisation)
+            it is td_panel_kernel against MEASURED_PEAKS.json hbm_gbs.
+  roofline_tridiag / roofline_stats   the other of the two
   cpu_baseline     the oracle port of the reference timed on this box's host cores on a bounded sample
 
 ``--impl reference`` times the reference algorithm's CPU implementation (the oracle port: /root/reference is
@@ -337,6 +339,37 @@ def run_ours(args, rank, world, local_rank):
         ach_tf = syrk_flops / (kt_syrk * 1e-3) / 1e12 if kt_syrk > 0 else 0.0
         ups = world * K / (dev_ms_max * 1e-3)
         e2e = world * K / (e2e_ms_max * 1e-3)
+        two_stage = n_panel < 0
+        rl_stats = {"kernel": "syrk_toeplitz_kernel (FP64 DMMA statistics, implicit Toeplitz operand)", "bound": "tensor",
+                    "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
+                    "frac": ach_tf / float(tf.value) if tf.value else None,
+                    "peak_source": "FP64 mma.sync m8n8k4 issue-rate microbenchmark run in this process "
+                                   "(MEASURED_PEAKS.json holds HBM and bf16 only)",
+                    "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
+                    "share_of_step": kt_syrk / (dev_ms_max / K) if dev_ms_max > 0 else None,
+                    "traffic": 1.029e9 * 4,
+                    "traffic_source": "profiles/r01_ncu_full_v2.txt (ncu --set full, one of the 4 launches per block: "
+                                      "6.8 MB read + 1.02 GB written)",
+                    "ncu_tensor_pipe_pct": 90.5}
+        if two_stage:
+            td_flops = 2.0 * 4.0 * n ** 3 / 3.0           # 4 n^3 / 3 per zone
+            td_ms = float(stage_acc.get("S5_tridiag", 0.0))
+            rl_td = {"kernel": "two-stage tridiagonalisation (band.cu: sb_panel_qr + DMMA gemm | sb2st_chase)",
+                     "bound": "tensor", "achieved": td_flops / (td_ms * 1e-3) / 1e12 if td_ms > 0 else 0.0,
+                     "peak": float(tf.value), "unit": "TFLOP/s",
+                     "frac": td_flops / (td_ms * 1e-3) / 1e12 / float(tf.value) if td_ms > 0 and tf.value else None,
+                     "algorithmic_flops_per_block": td_flops, "ms_per_block": td_ms,
+                     "dense_to_band_ms": kt_panel, "band_to_tridiagonal_ms": float(kt[3]),
+                     "note": "latency-bound stages (cluster QR columns, bulge-chasing steps) beside the DMMA GEMMs"}
+            roof, roof_other = rl_stats, {"roofline_tridiag": rl_td}
+        else:
+            rl_td = {"kernel": "td_panel_kernel (Householder tridiagonalisation, both zones)", "bound": "hbm",
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_block": td_bytes,
+                     "launches_per_block": n_panel, "kernel_ms_per_block": kt_panel, "traffic": None,
+                     "traffic_sample": {"source": "profiles/r01_ncu_full_v2.txt (ncu --set full, panel 5 of 128, cfg3)",
+                                        "dram_bytes": 8.165e9, "algorithmic_bytes": 7.874e9, "ratio": 1.04}}
+            roof, roof_other = (rl_td, {"roofline_stats": rl_stats}) if kt_panel > kt_syrk else (rl_stats, {"roofline_tridiag": rl_td})
         line = {
             "metric": "filter_updates_per_sec", "value": ups, "unit": "updates/s", "rtf": ups * H / FS,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True,
@@ -348,20 +381,10 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "updates/s", "rtf": e2e * H / FS, "ms_per_step": e2e_ms_max / K,
                     "h2d_bytes_per_step": 2 * H * 8, "d2h_bytes_per_step": (2 * V * H * L + 2 * H) * 8 + 32},
             "gpu_launches": launches,
-            "roofline": {"kernel": "td_panel_kernel (Householder tridiagonalisation, both zones)", "bound": "hbm",
-                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_block": td_bytes,
-                         "launches_per_block": n_panel, "kernel_ms_per_block": kt_panel, "traffic": None,
-                         "traffic_sample": {"source": "profiles/r01_ncu_full_v2.txt (ncu --set full, panel 5 of 128, cfg3)",
-                                            "dram_bytes": 8.165e9, "algorithmic_bytes": 7.874e9, "ratio": 1.04}},
-            "roofline_stats": {"kernel": "syrk_toeplitz_kernel (FP64 DMMA statistics)", "bound": "tensor",
-                               "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
-                               "frac": ach_tf / float(tf.value) if tf.value else None,
-                               "peak_source": "FP64 mma.sync m8n8k4 issue-rate microbenchmark run in this process",
-                               "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
-                               "ncu_tensor_pipe_pct": 90.5, "ncu_source": "profiles/r01_ncu_full_v2.txt"},
+            "roofline": roof,
             "stage_ms_last_block": stage_acc, "clocks": clocks, "checksum": chk,
         }
+        line.update(roof_other)
         line["alt_structured_stats"] = alt
         if world == 1 and not args.no_cpu_baseline:
             wl = make_workload(args.workload, n_blocks=8)

@@ -162,9 +162,10 @@ int apv_stage_times(apv_handle* h, float* ms7);
  * [0] Cholesky [1] two-sided reduction C = L^-1 R_B L^-T [2] tridiagonalisation
  * [3] bisection + inverse iteration [4] back-transformation [5] U = L^-T Q. */
 int apv_jdiag_phase_times(apv_handle* h, float* ms6);
-/* Device time of the two dominant kernels in the last block, milliseconds: [0] sum over all td_panel_kernel
- * launches (tridiagonalisation, HBM/L2 bound) [1] syrk_toeplitz_kernel (statistics, FP64 tensor bound)
- * [2] number of td_panel_kernel launches [3] reserved. */
+/* Device time of the dominant kernels in the last block, milliseconds: [1] syrk_toeplitz_kernel (statistics, FP64
+ * tensor bound).  One-stage tridiagonalisation (eig_mode 1): [0] sum over all td_panel_kernel launches (HBM/L2
+ * bound), [2] their number.  Two-stage (eig_mode 3 / auto for n >= 2048): [0] dense -> band (DMMA + cluster QR),
+ * [3] band -> tridiagonal (bulge chasing), [2] = -1. */
 int apv_kernel_times(apv_handle* h, float* ms4);
 /* CUDA-event timer on the handle's stream (the stream every kernel of the handle is launched on). */
 int apv_timer_start(apv_handle* h);
