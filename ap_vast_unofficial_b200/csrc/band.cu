@@ -11,11 +11,17 @@
 //     gemm (split-K)       Y = C22 V                                       (DMMA, skinny tile)
 //     sb_w1/w2_kernel      X = Y T,  W = X - 1/2 V T^T (V^T X),  panels Z1 = [V | W], Z2 = [W | V]
 //     gemm                 C22 -= Z1 Z2^T   (= V W^T + W V^T)              (DMMA)
-//   stage 2 (band -> tridiagonal), sb2st_chase_kernel: bulge chasing, one WARP per sweep, the 32x32 blocks in
-//     registers, sweeps pipelined two steps apart through progress counters in global memory (a sweep may run step
-//     k once its predecessor has finished step k + 1); the band (n x 64 doubles per zone) lives in L2.
+//     look-ahead: the next panel's columns are updated first (skinny GEMM) and its QR runs on a high-priority side
+//     stream beside the bulk of the rank-2b update.
+//   stage 2 (band -> tridiagonal), sb2st_chase_kernel: bulge chasing.  The critical path is 2 n dependent steps, so
+//     the step latency is everything: a CTA owns a group of 3 consecutive sweeps running as a wavefront on a sliding
+//     window of band rows in shared memory (two warps per sweep: off-diagonal block / diagonal block, the 32 x 32
+//     blocks in registers), a storer and a fetcher warp stream the window and hand the finished rows to the next
+//     group through release / acquire row bounds in global memory.  The band (n x 64 doubles per zone) lives in L2.
 //   back-transformation of the V wanted eigenvectors: sb2st_apply_q2_kernel (stage-2 reflectors, one CTA per
-//     vector, vector in shared memory), then the compact-WY kernel of jdiag.cu with the stage-1 reflectors.
+//     vector, vector in shared memory), then sb_apply_q1_kernel (stage-1 block reflectors with the panel T factors:
+//     every CTA keeps a slab of rows of all the vectors in shared memory, the reflector panels are streamed once).
+// APV_TS_DEBUG=1 prints per-kernel-class times (synchronising, no look-ahead) and in-kernel clock totals.
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -653,6 +659,135 @@ __global__ void __launch_bounds__(Q2T) sb2st_apply_q2_kernel(double* __restrict_
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Z <- Q1 Z with the stage-1 block reflectors  Q1 = P_0 P_1 ..,  P_p = I - V_p T_p V_p^T  (the compact-WY factors of
+// the panel QR), panels in descending order, for a chunk of Q1VC eigenvectors at a time.  The reflector panels are
+// streamed ONCE: a CTA owns a slab of Q1RS rows of all the vectors of the chunk (kept in shared memory for the whole
+// kernel) and per panel forms its part of S = V^T Z; one grid barrier per zone; every CTA sums the partial S, applies
+// T and updates its rows.  (One CTA per vector re-read every panel from L2: 17 GB of L2 traffic at n = 4096.)
+// Cooperative launch, grid = (n / Q1RS) CTAs per zone, 512 threads.
+constexpr int Q1T = 512;
+constexpr int Q1RS = 256;        // rows per CTA
+constexpr int Q1VC = 64;         // vectors per chunk
+constexpr int Q1VP = NB2 + 2;    // pitch of the staged reflector rows (even: 16-byte loads, conflict-free)
+
+struct SbQ1 {
+  const double* iv; const double* VH; const double* Tall; double* Zt; double* Sp; unsigned long long* bar;
+  int n, ldn, V, Vp, nz, npanels, v0;
+};
+
+__device__ __forceinline__ void q1_zone_sync(unsigned long long* bar, int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(bar, 1ull);
+    const unsigned long long target = (old / (unsigned long long)G + 1ull) * (unsigned long long)G;
+    while (*reinterpret_cast<volatile unsigned long long*>(bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(Q1T, 1) sb_apply_q1_kernel(SbQ1 a) {
+  extern __shared__ __align__(16) double q1sm[];
+  double* Zs = q1sm;                               // [Q1RS][Q1VC]   the slab of the vectors
+  double* Vs = Zs + Q1RS * Q1VC;                   // [Q1RS][Q1VP]   the slab of the current reflector panel
+  double* Us = Vs + Q1RS * Q1VP;                   // [NB2][Q1VC]    T V^T Z
+  const int nz = a.nz, z = blockIdx.x % nz, g = blockIdx.x / nz, G = gridDim.x / nz;
+  const int n = a.n, ldn = a.ldn, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R0 = g * Q1RS, nr = max(0, min(Q1RS, n - R0));
+  const int nv = min(Q1VC, a.V - a.v0);
+  const double* X = a.iv + (size_t)z * 6 * n * a.Vp + 4 * (size_t)n * a.Vp + a.v0;
+  for (int i = tid; i < Q1RS * Q1VC; i += Q1T) {
+    const int rr = i / Q1VC, v = i % Q1VC;
+    Zs[i] = (rr < nr && v < nv) ? X[(size_t)(R0 + rr) * a.Vp + v] : 0.0;
+  }
+  const double* vh = a.VH + (size_t)z * n * ldn;
+  double* Sp = a.Sp + (size_t)z * 2 * G * NB2 * Q1VC;
+  for (int p = a.npanels - 1; p >= 0; --p) {
+    const int j0 = p * NB2, r = j0 + NB2;
+    const bool active = R0 + nr > r;               // (the rows above r see zeros of V)
+    double* spg = Sp + ((size_t)(p & 1) * G + g) * NB2 * Q1VC;
+    __syncthreads();
+    if (active) {
+      // stage the panel rows of the slab: Vs[row][c] = v_{j0+c}[R0 + row]
+      for (int i = tid; i < NB2 * Q1RS; i += Q1T) {
+        const int c = i / Q1RS, rr = i % Q1RS;
+        Vs[rr * Q1VP + c] = (rr < nr) ? __ldg(vh + (size_t)(j0 + c) * ldn + R0 + rr) : 0.0;
+      }
+      __syncthreads();
+      // partial S[c][4 vq .. 4 vq + 3], c = lane, vq = warp
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const int rlo = max(0, r - R0);
+#pragma unroll 8
+      for (int rr = rlo; rr < nr; ++rr) {
+        const double vv = Vs[rr * Q1VP + lane];
+        const double2 za = *reinterpret_cast<const double2*>(Zs + rr * Q1VC + 4 * warp);
+        const double2 zb = *reinterpret_cast<const double2*>(Zs + rr * Q1VC + 4 * warp + 2);
+        s0 = fma(vv, za.x, s0); s1 = fma(vv, za.y, s1); s2 = fma(vv, zb.x, s2); s3 = fma(vv, zb.y, s3);
+      }
+      double* o = spg + lane * Q1VC + 4 * warp;
+      o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+    } else {
+      for (int i = tid; i < NB2 * Q1VC; i += Q1T) spg[i] = 0.0;
+    }
+    q1_zone_sync(a.bar + z, G);
+    if (!active) continue;
+    // S = sum of the partials, U = T S  (thread: row c = tid / 16 of U, vectors 4 (tid % 16) ..)
+    {
+      const int c = tid >> 4, v4 = (tid & 15) * 4;
+      // the summed S goes through shared memory (Us), then U = T S overwrites it
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      const double* sp = Sp + (size_t)(p & 1) * G * NB2 * Q1VC + c * Q1VC + v4;
+#pragma unroll 8
+      for (int q = 0; q < G; ++q) {
+        const double2 x0 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)q * NB2 * Q1VC));
+        const double2 x1 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)q * NB2 * Q1VC + 2));
+        t0 += x0.x; t1 += x0.y; t2 += x1.x; t3 += x1.y;
+      }
+      Us[c * Q1VC + v4] = t0; Us[c * Q1VC + v4 + 1] = t1; Us[c * Q1VC + v4 + 2] = t2; Us[c * Q1VC + v4 + 3] = t3;
+      __syncthreads();
+      const double* T = a.Tall + ((size_t)p * nz + z) * NB2 * NB2 + (size_t)c * NB2;       // row c of T (upper)
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll 8
+      for (int d = c; d < NB2; ++d) {
+        const double td = __ldg(T + d);
+        u0 = fma(td, Us[d * Q1VC + v4], u0); u1 = fma(td, Us[d * Q1VC + v4 + 1], u1);
+        u2 = fma(td, Us[d * Q1VC + v4 + 2], u2); u3 = fma(td, Us[d * Q1VC + v4 + 3], u3);
+      }
+      __syncthreads();
+      Us[c * Q1VC + v4] = u0; Us[c * Q1VC + v4 + 1] = u1; Us[c * Q1VC + v4 + 2] = u2; Us[c * Q1VC + v4 + 3] = u3;
+      __syncthreads();
+    }
+    // Z[row][v] -= sum_c V[row][c] U[c][v]:  thread: vector v = tid % 64 (U column in registers), rows tid / 64 + 8 k
+    {
+      const int v = tid & 63, rg = tid >> 6;
+      double u[NB2];
+#pragma unroll
+      for (int c = 0; c < NB2; ++c) u[c] = Us[c * Q1VC + v];
+      const int rlo = max(0, r - R0);
+#pragma unroll 2
+      for (int rr = rlo + rg; rr < nr; rr += Q1T / 64) {
+        const double2* vr = reinterpret_cast<const double2*>(Vs + rr * Q1VP);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB2; c += 2) {
+          const double2 vv = vr[c >> 1];
+          acc0 = fma(vv.x, u[c], acc0);
+          acc1 = fma(vv.y, u[c + 1], acc1);
+        }
+        Zs[rr * Q1VC + v] -= acc0 + acc1;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nv * Q1RS; i += Q1T) {
+    const int v = i / Q1RS, rr = i % Q1RS;
+    if (rr < nr) a.Zt[((size_t)z * a.V + a.v0 + v) * n + R0 + rr] = Zs[rr * Q1VC + v];
+  }
+}
+
 }  // namespace
 
 size_t twostage_scratch_bytes(int n, int nz, int nsplit_max) {
@@ -661,7 +796,7 @@ size_t twostage_scratch_bytes(int n, int nz, int nsplit_max) {
   d += (size_t)nz * nsplit_max * n * NB2;             // Ypart
   d += (size_t)nz * n * NB2;                          // X
   d += (size_t)nz * ceil_div(n, 64) * NB2 * NB2;      // Spart
-  d += (size_t)nz * NB2 * NB2;                        // Tp
+  d += (size_t)nz * ceil_div(n, NB2) * NB2 * NB2;     // T factors of all panels [panel][zone][NB2][NB2]
   d += (size_t)nz * n * LDB;                          // AB
   return d * sizeof(double) + (size_t)nz * n * sizeof(int);
 }
@@ -702,7 +837,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   double* X = Ypart + (size_t)nz * nsm * n * NB2;
   double* Spart = X + (size_t)nz * n * NB2;
   double* Tp = Spart + (size_t)nz * ceil_div(n, 64) * NB2 * NB2;
-  double* AB = Tp + (size_t)nz * NB2 * NB2;
+  double* AB = Tp + (size_t)nz * ceil_div(n, NB2) * NB2 * NB2;
   int* prog = reinterpret_cast<int*>(AB + (size_t)nz * n * LDB);
   int dev = 0, sms = 0;
   APV_CUDA_TRY(cudaGetDevice(&dev));
@@ -722,14 +857,12 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     int CS = 1;
     while (CS < QR_MAXCS && ceil_div(npn, CS) > max_rows) CS *= 2;
     if (npn > 64) CS = std::max(CS, 8);                       // spread the rows anyway: the column loop is latency-bound
-    static const int cs16_from = getenv("APV_QR_CS16") ? atoi(getenv("APV_QR_CS16")) : 1 << 30;
-    if (npn >= cs16_from) CS = 16;
     if (ceil_div(npn, CS) > max_rows) {
       snprintf(g_err, sizeof(g_err), "two-stage tridiagonalisation: n = %d exceeds the panel capacity", n);
       return EINVAL_;
     }
     SbPanel p;
-    p.Cm = ws.Cm; p.VH = ws.VH; p.VP = VP; p.tau = ws.tau; p.Tp = Tp;
+    p.Cm = ws.Cm; p.VH = ws.VH; p.VP = VP; p.tau = ws.tau; p.Tp = Tp + (size_t)(j0 / NB2) * nz * NB2 * NB2;
     p.n = n; p.ldn = ldn; p.j0 = j0; p.rows_per = ceil_div(npn, CS); p.dbg = dbg.on ? dclk : nullptr;
     const size_t smem = (size_t)p.rows_per * PP * sizeof(double);
     static thread_local size_t configured = 0;
@@ -770,7 +903,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     dbg.end(st, 1);
     ++*launches;
     SbW w;
-    w.Ypart = Ypart; w.VP = VP; w.Tp = Tp; w.X = X; w.Spart = Spart; w.Z1 = ws.Z1; w.Z2 = ws.Z2;
+    w.Ypart = Ypart; w.VP = VP; w.Tp = Tp + (size_t)(j0 / NB2) * nz * NB2 * NB2; w.X = X; w.Spart = Spart; w.Z1 = ws.Z1; w.Z2 = ws.Z2;
     w.n = n; w.r = r; w.npn = npn; w.nsplit = nsplit; w.nblk = ceil_div(npn, 64);
     dbg.begin(st);
     sb_w1_kernel<<<dim3(w.nblk, nz), 256, 0, st>>>(w);
@@ -883,6 +1016,35 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   ++*launches;
+  return OK;
+}
+
+// Eigenvectors of the band matrix (inverse-iteration workspace) -> eigenvectors of C (rows of Zt).
+int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches) {
+  const int n = ws.n, nz = ws.nz;
+  int npanels = 0;
+  for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) ++npanels;
+  const int G = ceil_div(n, Q1RS);
+  SbQ1 q;
+  q.iv = ws.iv; q.VH = ws.VH; q.Zt = ws.Zt;
+  q.Tall = ws.ts2 + (size_t)nz * n * NB2 * (2 + twostage_nsplit_max()) + (size_t)nz * ceil_div(n, 64) * NB2 * NB2;
+  // partial S buffers and the barrier counters live in the (then idle) Y slices of the band reduction
+  q.Sp = ws.ts2 + (size_t)nz * n * NB2;
+  q.bar = reinterpret_cast<unsigned long long*>(q.Sp + (size_t)nz * 2 * G * NB2 * Q1VC);
+  q.n = n; q.ldn = ws.ldn; q.V = ws.V; q.Vp = ws.Vp; q.nz = nz; q.npanels = npanels;
+  const size_t smem = (size_t)(Q1RS * Q1VC + Q1RS * Q1VP + NB2 * Q1VC) * sizeof(double);
+  static thread_local bool configured = false;
+  if (!configured) {
+    APV_CUDA_TRY(cudaFuncSetAttribute(sb_apply_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  APV_CUDA_TRY(cudaMemsetAsync(q.bar, 0, nz * sizeof(unsigned long long), st));
+  for (int v0 = 0; v0 < ws.V; v0 += Q1VC) {
+    q.v0 = v0;
+    void* args[] = {(void*)&q};
+    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb_apply_q1_kernel, dim3(G * nz), dim3(Q1T), args, smem, st));
+    ++*launches;
+  }
   return OK;
 }
 

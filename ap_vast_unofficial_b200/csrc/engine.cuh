@@ -62,6 +62,7 @@ size_t twostage_scratch_bytes(int n, int nz, int nsplit_max);
 int twostage_nsplit_max();
 int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches);
+int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches);   // then by the stage-1 block reflectors -> Zt
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
               cudaStream_t st, int* launches);
 

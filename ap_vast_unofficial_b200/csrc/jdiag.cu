@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(BTT) eig_backsolve_kernel(const double* __rest
 // stage, no clusters to repair; used where the matrix fits in one SM (2 n^2 doubles).
 constexpr int JACOBI_MAX_N = 112;
 constexpr int JACOBI_AUTO_N = 48;
-constexpr int TWOSTAGE_AUTO_N = 2048;   // eig_mode 0: two-stage tridiagonalisation (band.cu) from this size on
+constexpr int TWOSTAGE_AUTO_N = 1024;   // eig_mode 0: two-stage tridiagonalisation (band.cu) from this size on
 
 __global__ void __launch_bounds__(256) eig_jacobi_kernel(const double* __restrict__ Cm, double* __restrict__ lam,
                                                          double* __restrict__ Zt, int* __restrict__ info, int n, int ldn,
@@ -1172,11 +1172,15 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   }
   eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
   APV_CUDA_TRY(cudaEventRecord(ws.ev[4], st));
-  if (two_stage) APV_TRY(twostage_apply_q2(ws, st, &nl));
-  APV_TRY(ensure_smem(eig_backtransform_kernel, (size_t)n * sizeof(double)));
-  wy_tfactor_kernel<<<dim3(ceil_div(n, WYB), nz), 256, 0, st>>>(ws.VH, ws.tau, ws.Tf, n, ldn);
-  eig_backtransform_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.Tf, ws.Zt, n, ldn, V, ws.Vp);
-  ++nl;
+  if (two_stage) {
+    APV_TRY(twostage_apply_q2(ws, st, &nl));
+    APV_TRY(twostage_apply_q1(ws, st, &nl));
+  } else {
+    APV_TRY(ensure_smem(eig_backtransform_kernel, (size_t)n * sizeof(double)));
+    wy_tfactor_kernel<<<dim3(ceil_div(n, WYB), nz), 256, 0, st>>>(ws.VH, ws.tau, ws.Tf, n, ldn);
+    eig_backtransform_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.iv, ws.VH, ws.Tf, ws.Zt, n, ldn, V, ws.Vp);
+    ++nl;
+  }
   APV_CUDA_TRY(cudaEventRecord(ws.ev[5], st));
   APV_TRY(ensure_smem(eig_backsolve_kernel, (size_t)n * sizeof(double)));
   eig_backsolve_kernel<<<dim3(V, nz), BTT, (size_t)n * sizeof(double), st>>>(ws.Lm, ws.Dinv, ws.Zt, n, ldn, V, nblk);

@@ -49,7 +49,7 @@ typedef struct apv_config {
   int32_t perceptual;        /* 0: W == 1 (:326-327); 1: on-device masking model (apv_set_gain_table);
                                 2: weighting spectra supplied by the host per block (apv_set_weights) */
   int32_t normalize_gains;   /* EXPERIMENTAL_NORMALIZE_GAINS (:6,322-324)                           */
-  int32_t eig_mode;          /* 0 auto (2 for n <= 48, 3 for n >= 2048, else 1);
+  int32_t eig_mode;          /* 0 auto (2 for n <= 48, 3 for n >= 1024, else 1);
                                 1 one-stage Householder tridiagonalisation + bisection + inverse
                                   iteration (top-V);
                                 2 cyclic Jacobi (small n, full spectrum);
@@ -164,7 +164,7 @@ int apv_stage_times(apv_handle* h, float* ms7);
 int apv_jdiag_phase_times(apv_handle* h, float* ms6);
 /* Device time of the dominant kernels in the last block, milliseconds: [1] syrk_toeplitz_kernel (statistics, FP64
  * tensor bound).  One-stage tridiagonalisation (eig_mode 1): [0] sum over all td_panel_kernel launches (HBM/L2
- * bound), [2] their number.  Two-stage (eig_mode 3 / auto for n >= 2048): [0] dense -> band (DMMA + cluster QR),
+ * bound), [2] their number.  Two-stage (eig_mode 3 / auto for n >= 1024): [0] dense -> band (DMMA + cluster QR),
  * [3] band -> tridiagonal (bulge chasing), [2] = -1. */
 int apv_kernel_times(apv_handle* h, float* ms4);
 /* CUDA-event timer on the handle's stream (the stream every kernel of the handle is launched on). */
