@@ -248,30 +248,40 @@ __global__ void symmetrize_kernel(const double* __restrict__ in, double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Top-V eigenvalues of the symmetric tridiagonal (dd, ee) by multisection (32 Sturm counts per pass, one
-// warp per eigenvalue).  Count recurrence as LAPACK dlaebz.  grid (ceil(V/8), nz); smem 2n doubles.
+// Top-V eigenvalues of the symmetric tridiagonal (dd, ee) by multisection: one CTA per eigenvalue, 256 Sturm counts
+// per pass (7 passes from the Gershgorin interval to working precision instead of 53 bisections).  Count
+// recurrence as LAPACK dlaebz, with the quotient e^2 / t formed by a reciprocal and a product (the recurrence is a
+// chain of n dependent divisions: this halves its latency; the count is insensitive to the last ulp of t).
+// TPE threads per eigenvalue: 256 (one CTA per eigenvalue, grid (V, nz)) when few eigenvalues are wanted, 32 (one warp
+// per eigenvalue, grid (V / 8, nz)) for full-spectrum requests where throughput matters.  256 threads; smem 2n doubles.
+constexpr int BIS_T = 256;
+
 __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n,
                                            double x, double pivmin) {
   double t = d[0] - x;
   if (fabs(t) < pivmin) t = -pivmin;
   int c = (t <= 0.0);
+#pragma unroll 4
   for (int i = 1; i < n; ++i) {
-    t = d[i] - e2[i - 1] / t - x;
+    t = fma(-e2[i - 1], __drcp_rn(t), d[i] - x);
     if (fabs(t) < pivmin) t = -pivmin;
     c += (t <= 0.0);
   }
   return c;
 }
 
-__global__ void __launch_bounds__(256) eig_bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee,
-                                                         double* __restrict__ lam, double* __restrict__ tnorm, int n,
-                                                         int V) {
+template <int TPE>
+__global__ void __launch_bounds__(BIS_T) eig_bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee,
+                                                           double* __restrict__ lam, double* __restrict__ tnorm, int n,
+                                                           int V) {
   extern __shared__ double sm[];
   double* d = sm;
   double* e2 = sm + n;
   __shared__ double red[40];
   __shared__ double sh[4];
-  const int z = blockIdx.y;
+  __shared__ int first[BIS_T / 32];
+  constexpr int EPC = BIS_T / TPE;                 // eigenvalues per CTA
+  const int z = blockIdx.y, v = blockIdx.x * EPC + threadIdx.x / TPE, gt = threadIdx.x % TPE;
   const double* gd = dd + (size_t)z * n;
   const double* ge = ee + (size_t)z * n;
   double gl = DBL_MAX, gu = -DBL_MAX, emax = 0.0, onenrm = 0.0;
@@ -285,7 +295,6 @@ __global__ void __launch_bounds__(256) eig_bisect_kernel(const double* __restric
     emax = fmax(emax, er * er);
     onenrm = fmax(onenrm, fabs(di) + el + er);
   }
-  // block min/max via negated sums is awkward; do simple shared reductions
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = 16; o > 0; o >>= 1) {
     gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(256) eig_bisect_kernel(const double* __restric
   if (lane == 0) { red[warp] = gl; red[8 + warp] = gu; red[16 + warp] = emax; red[24 + warp] = onenrm; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < BIS_T / 32; ++w) {
       red[0] = fmin(red[0], red[w]); red[8] = fmax(red[8], red[8 + w]);
       red[16] = fmax(red[16], red[16 + w]); red[24] = fmax(red[24], red[24 + w]);
     }
@@ -308,32 +317,36 @@ __global__ void __launch_bounds__(256) eig_bisect_kernel(const double* __restric
     if (blockIdx.x == 0) { tnorm[z * 4 + 0] = red[24]; tnorm[z * 4 + 1] = sh[2]; tnorm[z * 4 + 2] = tn; }
   }
   __syncthreads();
-  const int v = blockIdx.x * 8 + warp;
-  if (v >= V) return;
+  if (TPE == 32 && v >= V) return;                 // (TPE == BIS_T: the grid is exact, the CTA stays convergent)
   const int k = n - v;            // k-th smallest (1-based)
   double lo = sh[0], hi = sh[1];
   const double pivmin = sh[2];
   const double atol = DBL_EPSILON * fmax(fabs(lo), fabs(hi));
-  for (int it = 0; it < 200; ++it) {
+  for (int it = 0; it < 100; ++it) {
     const double width = hi - lo;
     if (width <= fmax(fmax(atol, pivmin), 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)))) break;
-    const double h = width / 33.0;
-    const double x = lo + (lane + 1) * h;
+    const double h = width / (double)(TPE + 1);
+    const double x = lo + (gt + 1) * h;
     const int c = sturm_count(d, e2, n, x, pivmin);
     const unsigned mask = __ballot_sync(0xffffffffu, c >= k);
-    double nlo, nhi;
-    if (mask == 0u) {
-      nlo = __shfl_sync(0xffffffffu, x, 31);
-      nhi = hi;
+    int f;
+    if (TPE == 32) {
+      f = mask ? __ffs(mask) - 1 : TPE;
     } else {
-      const int f = __ffs(mask) - 1;
-      nhi = __shfl_sync(0xffffffffu, x, f);
-      nlo = f > 0 ? __shfl_sync(0xffffffffu, x, f - 1) : lo;
+      if (lane == 0) first[warp] = mask ? warp * 32 + __ffs(mask) - 1 : TPE;
+      __syncthreads();
+      f = TPE;
+#pragma unroll
+      for (int w = 0; w < BIS_T / 32; ++w) f = min(f, first[w]);
+      __syncthreads();
     }
+    // the eigenvalue lies in (x_{f-1}, x_f] with x_{-1} = lo, x_{TPE} = hi
+    const double nlo = f > 0 ? lo + f * h : lo;
+    const double nhi = f < TPE ? lo + (f + 1) * h : hi;
     if (!(nhi - nlo < width)) break;     // no progress at working precision
     lo = nlo; hi = nhi;
   }
-  if (lane == 0) lam[(size_t)z * V + v] = 0.5 * (lo + hi);
+  if (gt == 0) lam[(size_t)z * V + v] = 0.5 * (lo + hi);
 }
 
 // Shifts for inverse iteration: ascending walk, close values pushed apart by 10 eps |x| (LAPACK dstein).
@@ -1160,8 +1173,13 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));
   // ---- top-V eigenpairs of T
   double* tnorm = ws.shift + (size_t)nz * V;
-  APV_TRY(ensure_smem(eig_bisect_kernel, (size_t)2 * n * sizeof(double)));
-  eig_bisect_kernel<<<dim3(ceil_div(V, 8), nz), 256, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
+  if (V * nz <= 512) {
+    APV_TRY(ensure_smem(eig_bisect_kernel<BIS_T>, (size_t)2 * n * sizeof(double)));
+    eig_bisect_kernel<BIS_T><<<dim3(V, nz), BIS_T, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
+  } else {
+    APV_TRY(ensure_smem(eig_bisect_kernel<32>, (size_t)2 * n * sizeof(double)));
+    eig_bisect_kernel<32><<<dim3(ceil_div(V, 8), nz), BIS_T, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
+  }
   eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
   const size_t ivsm = (size_t)5 * n * sizeof(double) + (size_t)round_up(n, 16);
   if (ivsm <= 200 * 1024) {
