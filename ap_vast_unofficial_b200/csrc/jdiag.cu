@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(32) eig_invit_kernel(const double* __restrict_
 
 // Same algorithm with the per-vector work arrays in shared memory: one CTA per eigenvector, thread 0 runs the
 // sequential recurrences at shared-memory latency, the other threads do the fills, norms and scalings.
-// Used when 5 n doubles + n flags fit in one SM's shared memory (n <= ~5000).   grid (V, nz), 128 threads.
+// Used when 6 n doubles + n flags fit in one SM's shared memory (n <= ~4600).   grid (V, nz), 128 threads.
 __device__ __forceinline__ double hash_uniform(unsigned long long key) {
   unsigned long long x = key + 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -540,7 +540,8 @@ __global__ void __launch_bounds__(128) eig_invit_smem_kernel(const double* __res
   double* C = B + n;
   double* D2 = C + n;
   double* X = D2 + n;
-  unsigned char* IN = reinterpret_cast<unsigned char*>(X + n);
+  double* RA = X + n;          // reciprocals of the pivots
+  unsigned char* IN = reinterpret_cast<unsigned char*>(RA + n);
   __shared__ double red[8];
   __shared__ double sh[4];
   const int v = blockIdx.x, z = blockIdx.y;
@@ -563,39 +564,41 @@ __global__ void __launch_bounds__(128) eig_invit_smem_kernel(const double* __res
     X[i] = hash_uniform(((unsigned long long)(z * 131071 + v) << 32) ^ (unsigned long long)i);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {      // dlagtf
+  if (threadIdx.x == 0) {      // dlagtf; the running A[k], B[k] are carried in registers, one division per step
     double tolmax = 0.0;
-    double scale1 = fabs(A[0]) + fabs(B[0]);
+    double ak = A[0], bk = B[0];
+    double scale1 = fabs(ak) + fabs(bk);
     for (int k = 0; k < n - 1; ++k) {
-      double ak = A[k], ak1 = A[k + 1];
-      const double bk = B[k], ck = C[k];
+      const double ck = C[k], ak1 = A[k + 1];
       const double bk1 = (k < n - 2) ? B[k + 1] : 0.0;
-      double scale2 = fabs(ck) + fabs(ak1);
-      if (k < n - 2) scale2 += fabs(bk1);
-      const double piv1 = (ak == 0.0) ? 0.0 : fabs(ak) / scale1;
+      const double scale2 = fabs(ck) + fabs(ak1) + fabs(bk1);
+      double na = ak1, nb = bk1, oa = ak, ob = bk, d2k = 0.0;
       if (ck == 0.0) {
         scale1 = scale2;
+      } else if (ak != 0.0 && fabs(ck) * scale1 <= fabs(ak) * scale2) {      // piv2 <= piv1 without the quotients
+        scale1 = scale2;
+        const double m = ck / ak;
+        C[k] = m;
+        na = ak1 - m * bk;
       } else {
-        const double piv2 = fabs(ck) / scale2;
-        if (piv2 <= piv1) {
-          scale1 = scale2;
-          const double m = ck / ak;
-          C[k] = m;
-          A[k + 1] = ak1 - m * bk;
-        } else {
-          IN[k] = 1;
-          const double mult = ak / ck;
-          A[k] = ck;
-          A[k + 1] = bk - mult * ak1;
-          if (k < n - 2) {
-            D2[k] = bk1;
-            B[k + 1] = -mult * bk1;
-          }
-          B[k] = ak1;
-          C[k] = mult;
+        IN[k] = 1;
+        const double mult = ak / ck;
+        oa = ck;
+        na = bk - mult * ak1;
+        if (k < n - 2) {
+          d2k = bk1;
+          nb = -mult * bk1;
+          D2[k] = d2k;
         }
+        ob = ak1;
+        C[k] = mult;
+        A[k] = oa;
+        B[k] = ob;
       }
-      tolmax = fmax(tolmax, fmax(fabs(A[k]), fmax(fabs(B[k]), fabs(D2[k]))));
+      tolmax = fmax(tolmax, fmax(fabs(oa), fmax(fabs(ob), fabs(d2k))));
+      A[k + 1] = na;
+      if (k < n - 2) B[k + 1] = nb;
+      ak = na; bk = nb;
     }
     tolmax = fmax(tolmax, fabs(A[n - 1]));
     double tol = tolmax * eps;
@@ -603,6 +606,8 @@ __global__ void __launch_bounds__(128) eig_invit_smem_kernel(const double* __res
     sh[0] = tol;
     sh[1] = A[n - 1];
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) RA[i] = 1.0 / A[i];      // (inf for a zero pivot: never used then)
   __syncthreads();
   const double tol = sh[0], alast = sh[1];
   const double sfmin = DBL_MIN, bignum = 1.0 / DBL_MIN;
@@ -618,33 +623,47 @@ __global__ void __launch_bounds__(128) eig_invit_smem_kernel(const double* __res
     for (int i = threadIdx.x; i < n; i += blockDim.x) X[i] *= scl;
     __syncthreads();
     if (threadIdx.x == 0) {
-      // forward elimination (dlagts job = -1)
+      // forward elimination (dlagts job = -1), the running entry carried in a register
+      double xp = X[0];
       for (int k = 1; k < n; ++k) {
-        if (IN[k - 1] == 0) X[k] -= C[k - 1] * X[k - 1];
-        else {
-          const double t = X[k - 1];
-          X[k - 1] = X[k];
-          X[k] = t - C[k - 1] * X[k];
+        double xk = X[k];
+        const double c = C[k - 1];
+        if (IN[k - 1] == 0) {
+          xk = xk - c * xp;
+        } else {
+          const double t = xp;
+          xp = xk;
+          xk = t - c * xk;
         }
+        X[k - 1] = xp;
+        xp = xk;
       }
-      // back substitution with pivot perturbation
+      X[n - 1] = xp;
+      // back substitution with pivot perturbation; regular pivots are applied through their reciprocals
+      double x1 = 0.0, x2 = 0.0;          // X[k + 1], X[k + 2]  (B[n - 1] = D2[n - 2] = D2[n - 1] = 0)
       for (int k = n - 1; k >= 0; --k) {
-        double temp = X[k];
-        if (k <= n - 3) temp = temp - B[k] * X[k + 1] - D2[k] * X[k + 2];
-        else if (k == n - 2) temp = temp - B[k] * X[k + 1];
+        double temp = X[k] - B[k] * x1 - D2[k] * x2;
         double akk = A[k];
-        double pert = copysign(tol, akk);
-        for (;;) {
-          const double absak = fabs(akk);
-          if (absak < 1.0) {
-            if (absak < sfmin) {
-              if (absak == 0.0 || fabs(temp) * sfmin > absak) { akk += pert; pert *= 2.0; continue; }
-              temp *= bignum; akk *= bignum;
-            } else if (fabs(temp) > absak * bignum) { akk += pert; pert *= 2.0; continue; }
+        const double absk = fabs(akk);
+        double xk;
+        if (absk >= 1.0 || (absk >= sfmin && !(fabs(temp) > absk * bignum))) {
+          xk = temp * RA[k];
+        } else {
+          double pert = copysign(tol, akk);
+          for (;;) {
+            const double absak = fabs(akk);
+            if (absak < 1.0) {
+              if (absak < sfmin) {
+                if (absak == 0.0 || fabs(temp) * sfmin > absak) { akk += pert; pert *= 2.0; continue; }
+                temp *= bignum; akk *= bignum;
+              } else if (fabs(temp) > absak * bignum) { akk += pert; pert *= 2.0; continue; }
+            }
+            break;
           }
-          break;
+          xk = temp / akk;
         }
-        X[k] = temp / akk;
+        X[k] = xk;
+        x2 = x1; x1 = xk;
       }
     }
     __syncthreads();
@@ -1181,8 +1200,8 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     eig_bisect_kernel<32><<<dim3(ceil_div(V, 8), nz), BIS_T, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
   }
   eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
-  const size_t ivsm = (size_t)5 * n * sizeof(double) + (size_t)round_up(n, 16);
-  if (ivsm <= 200 * 1024) {
+  const size_t ivsm = (size_t)6 * n * sizeof(double) + (size_t)round_up(n, 16);
+  if (ivsm <= 220 * 1024) {
     APV_TRY(ensure_smem(eig_invit_smem_kernel, ivsm));
     eig_invit_smem_kernel<<<dim3(V, nz), 128, ivsm, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
   } else {
