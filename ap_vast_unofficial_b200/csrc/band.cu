@@ -193,6 +193,7 @@ struct SbW {
   const double* Ypart; const double* VP; const double* Tp;
   double* X; double* Spart; double* Z1; double* Z2;
   int n, r, npn, nsplit, nblk;
+  double* Cm; int ldn; int next_cols;     // look-ahead: also update the next panel's NB2 columns of C22 (sb_w2_kernel)
 };
 
 __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
@@ -246,8 +247,18 @@ __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
 }
 
 // W = X - V (1/2 T^T S),  S = sum of the partials;  Z1 = [V | W], Z2 = [W | V].   1024 threads (one entry of S each).
+// With next_cols the kernel also applies the rank-2b update to the NB2 leading columns of C22 (the next panel and
+// its diagonal block: C22[:, 0:NB2] -= V W0^T + W V0^T with the first NB2 rows W0, V0 of W and V, which every CTA
+// recomputes), so that the next panel factorisation can start without waiting for a separate GEMM.
 __global__ void __launch_bounds__(1024) sb_w2_kernel(SbW a) {
-  __shared__ double Ss[NB2][PP], Ms[NB2][PP], Ts[NB2][PP], Vs[64][PP];
+  extern __shared__ double w2sm[];
+  double (*Ss)[PP] = reinterpret_cast<double (*)[PP]>(w2sm);                       // S, later W0
+  double (*Ts)[PP] = reinterpret_cast<double (*)[PP]>(w2sm + NB2 * PP);            // T, later V0
+  double (*Ms)[PP] = reinterpret_cast<double (*)[PP]>(w2sm + 2 * NB2 * PP);
+  double (*Vs)[PP] = reinterpret_cast<double (*)[PP]>(w2sm + 3 * NB2 * PP);        // [64][PP]
+  double (*Ws)[PP] = reinterpret_cast<double (*)[PP]>(w2sm + (3 * NB2 + 64) * PP); // [64][PP]
+  double (*V0s)[PP] = Ts;
+  double (*W0s)[PP] = Ss;
   const int z = blockIdx.y, blk = blockIdx.x, n = a.n, t = threadIdx.x;
   {
     const double* sp = a.Spart + (size_t)z * a.nblk * NB2 * NB2 + t;
@@ -283,20 +294,50 @@ __global__ void __launch_bounds__(1024) sb_w2_kernel(SbW a) {
     Ms[p][c] = 0.5 * m;
   }
   __syncthreads();
-  if (!ok) return;
 #pragma unroll 8
   for (int p = 0; p < NB2; ++p) {
     const double v = Vs[row][p];
     x0 = fma(-v, Ms[p][cq], x0);
     x1 = fma(-v, Ms[p][cq + 1], x1);
   }
-  double* z1 = a.Z1 + ((size_t)z * n + gr) * 2 * NB2;
-  double* z2 = a.Z2 + ((size_t)z * n + gr) * 2 * NB2;
-  const double2 vv = make_double2(Vs[row][cq], Vs[row][cq + 1]), ww = make_double2(x0, x1);
-  *reinterpret_cast<double2*>(z1 + cq) = vv;
-  *reinterpret_cast<double2*>(z1 + NB2 + cq) = ww;
-  *reinterpret_cast<double2*>(z2 + cq) = ww;
-  *reinterpret_cast<double2*>(z2 + NB2 + cq) = vv;
+  if (ok) {
+    double* z1 = a.Z1 + ((size_t)z * n + gr) * 2 * NB2;
+    double* z2 = a.Z2 + ((size_t)z * n + gr) * 2 * NB2;
+    const double2 vv = make_double2(Vs[row][cq], Vs[row][cq + 1]), ww = make_double2(x0, x1);
+    *reinterpret_cast<double2*>(z1 + cq) = vv;
+    *reinterpret_cast<double2*>(z1 + NB2 + cq) = ww;
+    *reinterpret_cast<double2*>(z2 + cq) = ww;
+    *reinterpret_cast<double2*>(z2 + NB2 + cq) = vv;
+  }
+  if (!a.next_cols) return;
+  Ws[row][cq] = ok ? x0 : 0.0;
+  Ws[row][cq + 1] = ok ? x1 : 0.0;
+  {
+    const int i = t / NB2, c = t % NB2;          // (S and T are dead: their storage now holds W0 and V0)
+    V0s[i][c] = (a.r + i < n) ? a.VP[((size_t)z * n + a.r + i) * NB2 + c] : 0.0;
+  }
+  __syncthreads();
+  {   // W0 = X0 - V0 M  (first NB2 rows of W; same arithmetic as above)
+    const int i = t / NB2, c = t % NB2;
+    double w = (a.r + i < n) ? a.X[((size_t)z * n + a.r + i) * NB2 + c] : 0.0;
+#pragma unroll 8
+    for (int p = 0; p < NB2; ++p) w = fma(-V0s[i][p], Ms[p][c], w);
+    W0s[i][c] = w;
+  }
+  __syncthreads();
+  if (ok) {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < NB2; ++c) {
+      const double v = Vs[row][c], w = Ws[row][c];
+      acc0 = fma(v, W0s[cq][c], fma(w, V0s[cq][c], acc0));
+      acc1 = fma(v, W0s[cq + 1][c], fma(w, V0s[cq + 1][c], acc1));
+    }
+    double* cp = a.Cm + (size_t)z * n * a.ldn + (size_t)gr * a.ldn + a.r + cq;
+    double2 cv = *reinterpret_cast<double2*>(cp);
+    cv.x -= acc0; cv.y -= acc1;
+    *reinterpret_cast<double2*>(cp) = cv;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -905,9 +946,19 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     SbW w;
     w.Ypart = Ypart; w.VP = VP; w.Tp = Tp + (size_t)(j0 / NB2) * nz * NB2 * NB2; w.X = X; w.Spart = Spart; w.Z1 = ws.Z1; w.Z2 = ws.Z2;
     w.n = n; w.r = r; w.npn = npn; w.nsplit = nsplit; w.nblk = ceil_div(npn, 64);
+    const bool next_panel = n - r - NB2 >= 2;
+    w.Cm = ws.Cm; w.ldn = ldn; w.next_cols = (lookahead && next_panel) ? 1 : 0;
     dbg.begin(st);
     sb_w1_kernel<<<dim3(w.nblk, nz), 256, 0, st>>>(w);
-    sb_w2_kernel<<<dim3(w.nblk, nz), 1024, 0, st>>>(w);
+    {
+      const size_t w2smem = (size_t)(3 * NB2 + 2 * 64) * PP * sizeof(double);
+      static thread_local bool w2cfg = false;
+      if (!w2cfg) {
+        APV_CUDA_TRY(cudaFuncSetAttribute(sb_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w2smem));
+        w2cfg = true;
+      }
+      sb_w2_kernel<<<dim3(w.nblk, nz), 1024, w2smem, st>>>(w);
+    }
     dbg.end(st, 2);
     *launches += 2;
     // C22 -= V W^T + W V^T
@@ -918,12 +969,9 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     u.C = ws.Cm + (size_t)r * ldn + r; u.ldc = ldn; u.strideC = mstride;
     u.K = 2 * NB2; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
     u.bn = 64;                   // K = 64: two CTAs per SM hide the tile load / read-modify-write latency
-    const bool next_panel = n - r - NB2 >= 2;
     qr_done = false;
     if (lookahead && next_panel) {
-      GemmArgs c = u;            // the next panel's columns (its diagonal block and sub-diagonal panel)
-      c.M = npn; c.N = NB2;
-      APV_TRY(gemm_f64(c, st));
+      // (the next panel's columns -- its diagonal block and sub-diagonal panel -- were updated by sb_w2_kernel)
       APV_CUDA_TRY(cudaEventRecord(ws.ev2[2], st));
       APV_CUDA_TRY(cudaStreamWaitEvent(ws.st2, ws.ev2[2], 0));
       APV_TRY(launch_qr(r, ws.st2));
@@ -934,7 +982,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       u.tri = 1; u.mirror = 1;   // symmetric result: lower tiles computed, stored to both triangles
       APV_TRY(gemm_f64(u, st));
       APV_CUDA_TRY(cudaStreamWaitEvent(st, ws.ev2[3], 0));
-      *launches += 2;
+      ++*launches;
     } else {
       u.M = npn; u.N = npn;
       u.tri = 1; u.mirror = 1;
