@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
         scale = 1.0 / (alpha - beta);
       }
       const double q = fma(scale, g, rowj);     // lane > j: (v^T P)[lane];  lane < j: (V^T V)[lane][j]
-      tqs[lane] = tau * q;
+      // per-lane multiplier of the row update x <- x - v_r m: tau (v^T P) for the trailing columns, zero elsewhere
+      tqs[lane] = lane > j ? tau * q : 0.0;
       if (lane == 0) { scal[0] = scale; scal[1] = beta; }
       if (rank == 0) {
         if (lane < j) Gs[lane][j] = q;
@@ -118,13 +120,18 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       }
     }
     __syncthreads();
-    const double scale = scal[0], beta = scal[1], tq = tqs[lane];
-    SB_TICK(4);
-    // update of the rows below the diagonal fused with the partial Gram row of column j + 1
+    const double scale = scal[0], beta = scal[1], m1 = tqs[lane];
     double a4[4] = {0.0, 0.0, 0.0, 0.0};
     // rows of this warp: i = warp + QRW t; the rows gr = s0 + i <= j (leading rows of the first slabs) are finished
     int i = warp;
     if (s0 + i <= j) i += ((j - s0 - i) / QRW + 1) * QRW;
+    const bool isj = lane == j;
+    if (i < nr && s0 + i == j + 1) {       // the next diagonal row takes the update but is not part of the next Gram row
+      const double vr = slab[i * PP + j] * scale, x = slab[i * PP + lane];
+      __syncwarp();
+      slab[i * PP + lane] = isj ? vr : fma(-vr, m1, x);
+      i += QRW;
+    }
     for (; i < nr; i += 4 * QRW) {
       double x[4], pj[4];
 #pragma unroll
@@ -138,17 +145,16 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       for (int u = 0; u < 4; ++u) {
         const int ii = i + u * QRW;
         const double vr = pj[u] * scale;
-        if (lane > j) x[u] = fma(-vr, tq, x[u]);
-        else if (lane == j) x[u] = vr;
-        if (ii < nr && lane >= j) slab[ii * PP + lane] = x[u];
+        x[u] = isj ? vr : fma(-vr, m1, x[u]);       // column j keeps the reflector, the lanes < j have m1 = 0
+        if (ii < nr) slab[ii * PP + lane] = x[u];
         const double xb = __shfl_sync(0xffffffffu, x[u], (j + 1) & 31);
-        if (s0 + ii > j + 1) a4[u] = fma(x[u], xb, a4[u]);       // (rows beyond the slab hold zeros)
+        a4[u] = fma(x[u], xb, a4[u]);                             // (rows beyond the slab hold zeros)
       }
     }
     acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     if (j >= s0 && j < s1 && warp == 0) {            // diagonal row: R
       double x = slab[(j - s0) * PP + lane];
-      if (lane > j) x -= tq;
+      if (lane > j) x -= m1;                       // v_j = 1 on the diagonal row
       else if (lane == j) x = beta;
       slab[(j - s0) * PP + lane] = x;
     }
@@ -845,6 +851,19 @@ size_t twostage_scratch_bytes(int n, int nz, int nsplit_max) {
 int twostage_nsplit_max() { return 8; }
 
 // APV_TS_DEBUG=1: synchronous per-kernel-class timing of the two-stage reduction, printed to stderr.
+struct TsTrace {        // APV_TS_DEBUG=2: events on the main stream around every kernel class, read after the loop
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  size_t used = 0;
+  void mark(cudaStream_t st, int c) {
+    if (!on) return;
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); cls.push_back(0); }
+    cls[used] = c;
+    cudaEventRecord(ev[used++], st);
+  }
+};
+
 struct TsDebug {
   bool on = false;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -887,9 +906,13 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   APV_CUDA_TRY(cudaMemsetAsync(prog, 0, (size_t)nz * n * sizeof(int), st));
 
   // ---- stage 1
-  // Look-ahead: as soon as panel k's W is known, the NB2 columns of the next panel are updated on their own
-  // (a skinny GEMM), the next panel's QR (latency-bound, one cluster per zone) starts on a high-priority side
-  // stream, and the bulk of the rank-2b update (all the other SMs) runs beside it on the main stream.
+  // Look-ahead: as soon as panel k's W is known, the NB2 columns of the next panel are updated on their own (inside
+  // sb_w2_kernel), the next panel's QR (latency-bound, one cluster per zone) starts, and the bulk of the rank-2b
+  // update (all the other SMs) runs beside it on a side stream.
+  static TsTrace tr;
+  tr.on = getenv("APV_TS_DEBUG") && atoi(getenv("APV_TS_DEBUG")) == 2;
+  tr.used = 0;
+  if (tr.on) dbg.on = false;
   const bool lookahead = !dbg.on && ws.st2 != nullptr && !getenv("APV_TS_NO_LOOKAHEAD");
   auto launch_qr = [&](int j0, cudaStream_t qs) -> int {
     const int r = j0 + NB2, npn = n - r;
@@ -928,7 +951,9 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   bool qr_done = false;          // the QR of the current panel was issued by the previous iteration (look-ahead)
   for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) {
     const int r = j0 + NB2, npn = n - r;
+    tr.mark(st, 0);            // [0] join with the look-ahead QR / own QR
     if (!qr_done) APV_TRY(launch_qr(j0, st));
+    tr.mark(st, 1);            // [1] Y
     // Y = C22 V in K slices
     int nsplit = std::max(1, std::min(nsm, (2 * sms) / std::max(1, nz * ceil_div(npn, 128))));
     const int kslice = round_up(ceil_div(npn, nsplit), 16);
@@ -943,6 +968,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     APV_TRY(gemm_f64(y, st));
     dbg.end(st, 1);
     ++*launches;
+    tr.mark(st, 2);            // [2] W (+ next panel's columns)
     SbW w;
     w.Ypart = Ypart; w.VP = VP; w.Tp = Tp + (size_t)(j0 / NB2) * nz * NB2 * NB2; w.X = X; w.Spart = Spart; w.Z1 = ws.Z1; w.Z2 = ws.Z2;
     w.n = n; w.r = r; w.npn = npn; w.nsplit = nsplit; w.nblk = ceil_div(npn, 64);
@@ -961,6 +987,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     }
     dbg.end(st, 2);
     *launches += 2;
+    tr.mark(st, 3);            // [3] look-ahead QR (the rank-2b update runs beside it on the side stream)
     // C22 -= V W^T + W V^T
     GemmArgs u{};
     u.batch = nz;
@@ -972,15 +999,18 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     qr_done = false;
     if (lookahead && next_panel) {
       // (the next panel's columns -- its diagonal block and sub-diagonal panel -- were updated by sb_w2_kernel)
+      // The panel QR goes first, in order on the main stream, so that its clusters find free SMs; the bulk of the
+      // update follows on the side stream and fills the rest of the chip; the main stream joins it before Y.
       APV_CUDA_TRY(cudaEventRecord(ws.ev2[2], st));
-      APV_CUDA_TRY(cudaStreamWaitEvent(ws.st2, ws.ev2[2], 0));
-      APV_TRY(launch_qr(r, ws.st2));
-      APV_CUDA_TRY(cudaEventRecord(ws.ev2[3], ws.st2));
+      APV_TRY(launch_qr(r, st));
       qr_done = true;
+      APV_CUDA_TRY(cudaStreamWaitEvent(ws.st2, ws.ev2[2], 0));
       u.A += (size_t)NB2 * 2 * NB2; u.B += (size_t)NB2 * 2 * NB2; u.C += (size_t)NB2 * ldn + NB2;
       u.M = npn - NB2; u.N = npn - NB2;
       u.tri = 1; u.mirror = 1;   // symmetric result: lower tiles computed, stored to both triangles
-      APV_TRY(gemm_f64(u, st));
+      APV_TRY(gemm_f64(u, ws.st2));
+      APV_CUDA_TRY(cudaEventRecord(ws.ev2[3], ws.st2));
+      tr.mark(st, 4);          // [4] waiting for the update after the look-ahead QR
       APV_CUDA_TRY(cudaStreamWaitEvent(st, ws.ev2[3], 0));
       ++*launches;
     } else {
@@ -991,6 +1021,18 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       dbg.end(st, 3);
       ++*launches;
     }
+  }
+  tr.mark(st, 5);
+  if (tr.on) {
+    cudaStreamSynchronize(st);
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i + 1 < tr.used; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tr.ev[i], tr.ev[i + 1]);
+      acc[tr.cls[i]] += ms;
+    }
+    fprintf(stderr, "two-stage main-stream ms (look-ahead on): first QR %.2f | Y %.2f | W %.2f | look-ahead QR %.2f | wait for the update %.2f\n",
+            acc[0], acc[1], acc[2], acc[3], acc[4]);
   }
   APV_CUDA_TRY(cudaEventRecord(ws.ev2[0], st));
   // ---- stage 2
