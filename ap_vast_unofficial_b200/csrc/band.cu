@@ -179,14 +179,20 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   if (rank == 0) {
     if (warp == 0) {
       a.tau[(size_t)z * n + j0 + lane] = taus[lane];
-      // T (dlarft, forward / columnwise): lane = row of T;  T[r][i] = -tau_i sum_{k=r}^{i-1} T[r][k] G[k][i]
+      // T = (diag(1 / tau) + striu(V^T V))^-1 (the dlarft factor): lane = column c, back substitution
+      //   t[c] = tau_c,  t[r] = -tau_r sum_{k = r+1 .. c} G[r][k] t[k]  (r < c),  zero below the diagonal
       double* Tp = a.Tp + (size_t)z * NB2 * NB2;
-      for (int i = 0; i < NB2; ++i) {
-        double t = 0.0;
-        for (int k = lane; k < i; ++k) t = fma(Tsm[lane][k], Gs[k][i], t);
-        const double v = (lane == i) ? taus[i] : (lane < i ? -taus[i] * t : 0.0);
-        Tsm[lane][i] = v;          // (row `lane` is private to this lane)
-        Tp[lane * NB2 + i] = v;
+      for (int r = NB2 - 1; r >= 0; --r) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = r + 1;
+        for (; k + 1 < NB2; k += 2) {
+          a0 = fma(Gs[r][k], Tsm[k][lane], a0);                  // (Tsm[k][lane] = 0 for k > lane)
+          a1 = fma(Gs[r][k + 1], Tsm[k + 1][lane], a1);
+        }
+        if (k < NB2) a0 = fma(Gs[r][k], Tsm[k][lane], a0);
+        const double t = (r == lane) ? taus[r] : (r < lane ? -taus[r] * (a0 + a1) : 0.0);
+        Tsm[r][lane] = t;                                        // (column `lane` is private to this lane)
+        Tp[r * NB2 + lane] = t;
       }
     }
   }
