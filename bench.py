@@ -228,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
     sh = full["shapes"]
     H = sh["H"]
     t0, t1 = block_ranges(nblk_total, world)[rank]
-    need = W + 2 * K + 2
+    need = W + 2 * K + 3
     start = min(t0, max(0, nblk_total - need))
     sigA = full["signal_A"][start * H:(start + need) * H]
     sigB = full["signal_B"][start * H:(start + need) * H]
@@ -278,13 +278,21 @@ def run_ours(args, rank, world, local_rank):
     stage_acc = eng.stage_times()
 
     # ---- timed region 2: end to end through the drop-in call, host buffers in, host buffers out
+    # (one untimed call first: the host path's pinned staging buffer is allocated on first use)
+    eng.process_input_buffers(sigA[blk * H:(blk + 1) * H], sigB[blk * H:(blk + 1) * H])
+    blk += 1
     barrier()
     te0 = time.perf_counter()
     chk = 0.0
+    trace = []
     for _ in range(K):
+        tc0 = time.perf_counter()
         oA, oB, oAt, oBt = eng.process_input_buffers(sigA[blk * H:(blk + 1) * H], sigB[blk * H:(blk + 1) * H])
         chk += float(oA[0][0, 0])
         blk += 1
+        trace.append(1e3 * (time.perf_counter() - tc0))
+    if os.environ.get("APV_BENCH_TRACE"):
+        print("e2e per-call ms:", " ".join("%.1f" % x for x in trace), file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te0
     barrier()
