@@ -713,6 +713,105 @@ __global__ void __launch_bounds__(Q2T) sb2st_apply_q2_kernel(double* __restrict_
 
 
 // ------------------------------------------------------------------------------------------------
+// Z <- Q2 Z, wavefront form for a handful of eigenvectors (V <= Q2W_MAXV): lane = eigenvector, so a reflector is
+// applied with thread-local dot products -- no shuffles, no CTA barriers.  A warp owns a CHAIN: the 32 consecutive
+// sweeps [S, S+32) for 32 vectors, and walks down the band in blocks k = 0, 1, ..: block k applies the reflectors
+// (s, k), s = S+31 .. S, which act on the rows [S+1+32k, S+64+32k) -- a window of 63 rows per lane in registers
+// that slides by 32 rows per block.  Chain S may run block k once chain S+32 has finished block k (the reflectors of
+// the higher sweeps come first); finished rows travel between chains through global memory with release /
+// acquire block counters, like the rows of the bulge chasing.  The reflectors of a block (32 x 32 doubles) are
+// staged in shared memory and read as broadcasts.  Cooperative launch, 128 threads, one chain per warp.
+constexpr int Q2W_T = 128;
+constexpr int Q2W_MAXV = 128;
+
+struct SbQ2 {
+  double* iv; const double* V2; int* prog;
+  int n, ldn, Vp, nz, ngrp, nhalf;
+};
+
+__global__ void __launch_bounds__(Q2W_T, 1) sb2st_apply_q2_wave_kernel(SbQ2 a) {
+  __shared__ __align__(16) double vs_all[Q2W_T / 32][32][34];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n = a.n, ldn = a.ldn, Vp = a.Vp;
+  const int nprob = a.nz * a.nhalf;
+  const int gw = blockIdx.x * (Q2W_T / 32) + wib, GW = gridDim.x * (Q2W_T / 32);
+  const int prob = gw % nprob, wp = gw / nprob, Gp = GW / nprob;      // warps are dealt round-robin to the problems
+  if (wp >= Gp) return;
+  const int z = prob / a.nhalf, h = prob % a.nhalf;
+  double* X = a.iv + (size_t)z * 6 * n * Vp + 4 * (size_t)n * Vp + 32 * h + lane;       // X[i * Vp]
+  const double* v2 = a.V2 + (size_t)z * n * ldn;
+  int* prog = a.prog + (size_t)prob * a.ngrp;
+  double (*vs)[34] = vs_all[wib];
+  for (int c = wp; c < a.ngrp; c += Gp) {          // chains in descending sweep order
+    const int gi = a.ngrp - 1 - c, S = gi * NB2;
+    const int K = 1 + (n - S - 2) / NB2;            // blocks of this chain (= steps of its first sweep)
+    double w[63];
+    for (int k = 0; k < K; ++k) {
+      const int base = S + 1 + k * NB2;             // first row of the window
+      if (gi + 1 < a.ngrp) {                        // the chain above must have finished block k
+        if (lane == 0) {
+          int v;
+          for (;;) {
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog + gi + 1) : "memory");
+            if (v >= k + 1) break;
+            __nanosleep(32);
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
+      // stage the block's reflectors: vs[o][i] = V2[S + o][base + o + i]  (entry 0 holds tau); zero beyond the matrix
+#pragma unroll 8
+      for (int o = 0; o < 32; ++o) {
+        const int s = S + o, row = base + o + lane;
+        vs[o][lane] = (s <= n - 3 && row < n) ? __ldcg(v2 + (size_t)s * ldn + row) : 0.0;
+      }
+      // rows entering the window
+      if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < 63; ++j) w[j] = (base + j < n) ? __ldcg(X + (size_t)(base + j) * Vp) : 0.0;
+      } else {
+#pragma unroll
+        for (int j = 31; j < 63; ++j) w[j] = (base + j < n) ? __ldcg(X + (size_t)(base + j) * Vp) : 0.0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 31; o >= 0; --o) {
+        if (S + o <= n - 3 && base + o < n) {        // warp-uniform: the reflector exists
+          const double tau = vs[o][0];
+          double d0 = w[o], d1 = 0.0;                // v_0 = 1
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) {
+            const double2 vv = *reinterpret_cast<const double2*>(&vs[o][i]);
+            d0 = fma(vv.x, w[o + i], d0);
+            d1 = fma(vv.y, w[o + i + 1], d1);
+          }
+          d1 = fma(vs[o][1], w[o + 1], d1);
+          const double td = tau * (d0 + d1);
+          w[o] -= td;
+          w[o + 1] = fma(-td, vs[o][1], w[o + 1]);
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) {
+            const double2 vv = *reinterpret_cast<const double2*>(&vs[o][i]);
+            w[o + i] = fma(-td, vv.x, w[o + i]);
+            w[o + i + 1] = fma(-td, vv.y, w[o + i + 1]);
+          }
+        }
+      }
+      // rows leaving the window are final for this chain (all of it after the last block)
+      const int nout = (k + 1 == K) ? 63 : 32;
+#pragma unroll
+      for (int j = 0; j < 63; ++j)
+        if (j < nout && base + j < n) X[(size_t)(base + j) * Vp] = w[j];
+#pragma unroll
+      for (int j = 0; j < 31; ++j) w[j] = w[j + 32];
+      __syncwarp();
+      if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prog + gi), "r"(k + 1 == K ? PROG_DONE : k + 1) : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Z <- Q1 Z with the stage-1 block reflectors  Q1 = P_0 P_1 ..,  P_p = I - V_p T_p V_p^T  (the compact-WY factors of
 // the panel QR), panels in descending order, for a chunk of Q1VC eigenvectors at a time.  The reflector panels are
 // streamed ONCE: a CTA owns a slab of Q1RS rows of all the vectors of the chunk (kept in shared memory for the whole
@@ -1103,7 +1202,26 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool dbg = getenv("APV_TS_DEBUG") != nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-  sb2st_apply_q2_kernel<<<dim3(ws.V, ws.nz), Q2T, smem, st>>>(ws.iv, ws.Tm, n, ws.ldn, ws.Vp);
+  if (ws.V <= Q2W_MAXV && !getenv("APV_Q2_PER_VECTOR")) {
+    // few vectors: wavefront of chains, lane = vector (the per-vector kernel pays a CTA barrier per sweep)
+    SbQ2 q;
+    q.iv = ws.iv; q.V2 = ws.Tm; q.n = n; q.ldn = ws.ldn; q.Vp = ws.Vp; q.nz = ws.nz;
+    q.ngrp = ceil_div(n - 2, NB2); q.nhalf = ws.Vp / 32;
+    // the block counters live in the (then idle) Y slices of the band reduction
+    q.prog = reinterpret_cast<int*>(ws.ts2 + (size_t)ws.nz * n * NB2);
+    const int nprob = q.nz * q.nhalf;
+    APV_CUDA_TRY(cudaMemsetAsync(q.prog, 0, (size_t)nprob * q.ngrp * sizeof(int), st));
+    int dev = 0, sms = 0;
+    APV_CUDA_TRY(cudaGetDevice(&dev));
+    APV_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // one warp per chain in flight: at most ngrp chains per problem, at most one CTA per SM
+    const int warps = std::min(nprob * q.ngrp, sms * (Q2W_T / 32) / nprob * nprob);
+    const int grid = std::max(1, ceil_div(std::max(warps, nprob), Q2W_T / 32));
+    void* args[] = {(void*)&q};
+    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb2st_apply_q2_wave_kernel, dim3(grid), dim3(Q2W_T), args, 0, st));
+  } else {
+    sb2st_apply_q2_kernel<<<dim3(ws.V, ws.nz), Q2T, smem, st>>>(ws.iv, ws.Tm, n, ws.ldn, ws.Vp);
+  }
   APV_CUDA_TRY(cudaGetLastError());
   if (dbg) {
     float ms = 0.f;

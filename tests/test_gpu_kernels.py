@@ -109,3 +109,30 @@ def test_dmma_peak_reports():
     capi.check(capi.lib().apv_bench_dmma_peak(2000, C.byref(tf)))
     print("DMMA peak TFLOP/s:", tf.value)
     assert tf.value > 1.0
+
+
+def test_dfma_rate_reports():
+    """CUDA-core FP64 next to the tensor pipe (decides how much scalar FP64 the latency-bound kernels can afford)."""
+    capi = _capi()
+    o = (C.c_double * 3)()
+    capi.check(capi.lib().apv_bench_dfma(1000, o))
+    print("DFMA TFLOP/s %.1f, %.1f cycles per dependent DFMA" % (o[0], o[1]))
+    assert o[0] > 1.0 and 2.0 < o[1] < 64.0
+
+
+@pytest.mark.parametrize("n", [96, 200, 1000])
+def test_two_stage_matches_one_stage(n):
+    """The two tridiagonalisation routes give the same eigenvalues (to rounding) and the same filters."""
+    from ap_vast_unofficial_b200 import jdiag
+    rng = np.random.default_rng(n)
+    A, B = _spd_pair(n, rng)
+    V = min(n, 48)
+    U1, D1 = jdiag(A, B, number_of_eigenvectors=V, eig_mode=1)
+    U3, D3 = jdiag(A, B, number_of_eigenvectors=V, eig_mode=3)
+    l1, l3 = np.diag(D1), np.diag(D3)
+    assert np.max(np.abs(l1 - l3)) / l1[0] < 1e-13
+    r = rng.standard_normal(n)
+    w1 = np.cumsum(U1 * ((U1.T @ r) / (l1 + 0.7))[None, :], axis=1)
+    w3 = np.cumsum(U3 * ((U3.T @ r) / (l3 + 0.7))[None, :], axis=1)
+    err = np.linalg.norm(w1 - w3, axis=0) / np.linalg.norm(w1, axis=0)
+    assert err.max() < 1e-8, err.max()

@@ -27,11 +27,12 @@ def _check(res, name, wtol=1e-8):
             assert v <= tol, (name, t, k, v)
 
 
-@pytest.mark.parametrize("eig_mode", [1, 2])
+@pytest.mark.parametrize("eig_mode", [1, 2, 3])
 @pytest.mark.parametrize("name", ["tiny", "tiny_hop", "tiny_runA", "mid"])
 def test_golden_small(name, eig_mode):
     """eig_mode 1 = tridiagonalisation + bisection + inverse iteration, 2 = shared-memory Jacobi (n <= 112; "mid" with
-    n = 128 falls back to the tridiagonal path)."""
+    n = 128 falls back to the tridiagonal path), 3 = two-stage tridiagonalisation (band reduction + bulge chasing; the
+    automatic choice from n = 1024 on, forced here on the small golden cases)."""
     eng, g, res = replay(_engine(), name, extra_ctor=dict(eig_mode=eig_mode))
     _check(res, name)
     for a, v in compare_state(eng, g).items():
@@ -52,7 +53,7 @@ def test_golden_structured_statistics(name):
     _check(res, name + "-structured")
 
 
-@pytest.mark.parametrize("eig_mode", [1, 2])
+@pytest.mark.parametrize("eig_mode", [1, 2, 3])
 def test_golden_full_rank_closed_form(eig_mode):
     """V = n: per-rank filters inside a degenerate eigenvalue cluster are basis-dependent (sign/rotation
     ambiguity, as for eigenvectors), so ranks are compared only where the eigenvalue gap is resolved; the
