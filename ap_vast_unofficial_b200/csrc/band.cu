@@ -209,7 +209,9 @@ struct SbW {
 };
 
 __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
-  __shared__ double Ys[64][PP], Vs[64][PP], Ts[NB2][PP];
+  constexpr int WP = NB2 + 4;      // even pitch: 16-byte shared loads of row segments
+  __shared__ __align__(16) double Ys[64][WP], Ts[NB2][WP];
+  __shared__ double Vs[64][PP];
   const int z = blockIdx.y, blk = blockIdx.x, n = a.n;
   const int row = threadIdx.x >> 2, cq = (threadIdx.x & 3) * 8;
   const int gr = a.r + blk * 64 + row;                       // global row
@@ -218,12 +220,18 @@ __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
   double y[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) y[c] = 0.0;
-  if (ok)
-    for (int s = 0; s < a.nsplit; ++s) {
-      const double* yp = a.Ypart + ((size_t)(z * a.nsplit + s) * n + gr) * NB2 + cq;
+  if (ok) {
+    const double2* yp = reinterpret_cast<const double2*>(a.Ypart + ((size_t)z * a.nsplit * n + gr) * NB2 + cq);
+    const size_t sstride = (size_t)n * NB2 / 2;
+#pragma unroll 4
+    for (int s = 0; s < a.nsplit; ++s) {       // (all the slices' loads in flight together)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) y[c] += yp[c];
+      for (int c = 0; c < 4; ++c) {
+        const double2 t = yp[s * sstride + c];
+        y[2 * c] += t.x; y[2 * c + 1] += t.y;
+      }
     }
+  }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     Ys[row][cq + c] = y[c];
@@ -233,10 +241,16 @@ __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
   double x[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) x[c] = 0.0;
+#pragma unroll 8
   for (int k = 0; k < NB2; ++k) {
     const double yk = Ys[row][k];
+    const double2* tr = reinterpret_cast<const double2*>(&Ts[k][cq]);      // T is upper triangular (zeros stored)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x[c] = fma(yk, Ts[k][cq + c], x[c]);     // T is upper triangular (zeros stored)
+    for (int c = 0; c < 4; ++c) {
+      const double2 t = tr[c];
+      x[2 * c] = fma(yk, t.x, x[2 * c]);
+      x[2 * c + 1] = fma(yk, t.y, x[2 * c + 1]);
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -248,10 +262,13 @@ __global__ void __launch_bounds__(256) sb_w1_kernel(SbW a) {
   // S_partial[p][c] = sum_rows V[row][p] X[row][c]:  thread -> p = tid / 8, c = (tid % 8) * 4 .. + 3
   const int p = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
   double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
   for (int i = 0; i < 64; ++i) {
     const double v = Vs[i][p];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) s4[c] = fma(v, Ys[i][c0 + c], s4[c]);
+    const double2 xa = *reinterpret_cast<const double2*>(&Ys[i][c0]);
+    const double2 xb = *reinterpret_cast<const double2*>(&Ys[i][c0 + 2]);
+    s4[0] = fma(v, xa.x, s4[0]); s4[1] = fma(v, xa.y, s4[1]);
+    s4[2] = fma(v, xb.x, s4[2]); s4[3] = fma(v, xb.y, s4[3]);
   }
   double* sp = a.Spart + ((size_t)(z * a.nblk + blk) * NB2 + p) * NB2 + c0;
 #pragma unroll
@@ -276,6 +293,13 @@ __global__ void __launch_bounds__(1024) sb_w2_kernel(SbW a) {
     const double* sp = a.Spart + (size_t)z * a.nblk * NB2 * NB2 + t;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int b = 0;
+    for (; b + 15 < a.nblk; b += 16) {          // 16 partials in flight (the loop is a chain of L2 round trips otherwise)
+      double t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = sp[(size_t)(b + u) * NB2 * NB2];
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) { s0 += t[u]; s1 += t[u + 1]; s2 += t[u + 2]; s3 += t[u + 3]; }
+    }
     for (; b + 3 < a.nblk; b += 4) {
       s0 += sp[(size_t)b * NB2 * NB2];
       s1 += sp[(size_t)(b + 1) * NB2 * NB2];
