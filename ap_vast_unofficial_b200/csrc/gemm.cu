@@ -161,24 +161,34 @@ __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_kernel(GemmArgs g
 }
 
 // ------------------------------------------------------------------------------------------------
-// Skinny product C[M x N <= 32] = alpha A[M x K] B[K x N] + beta C (no transposes): the band reduction's
-// Y = C22 V reads an n' x n' matrix once for 32 columns of output, i.e. it is a STREAM of A (8 flops per byte) and
-// has to keep HBM busy.  Same 128 x 32 DMMA tile as gemm_kernel<0, 0, 32>, but the tiles are staged by cp.async
-// (16-byte copies, zero fill at the edges) through a ring of SK_STAGES shared-memory stages, so every CTA keeps
-// SK_STAGES - 1 tiles (20 KB each) in flight; two CTAs per SM.  (Register-staged version: 1.8 TB/s at n' = 4000.)
-constexpr int SK_STAGES = 4;
-constexpr int SK_BN = 32, SK_LDA = BK + 4, SK_LDB = SK_BN + 4;
-constexpr int SK_STAGE_DOUBLES = BM * SK_LDA + BK * SK_LDB;
-constexpr int SK_SMEM_BYTES = SK_STAGES * SK_STAGE_DOUBLES * (int)sizeof(double);
+// cp.async variant of the 128 x 64 and 128 x 32 tiles for op(A) = A (row-major M x K) with 16-byte aligned rows:
+// the operand tiles are staged by 16-byte cp.async copies (zero fill at the edges) through a ring of shared-memory
+// stages, so a CTA keeps STAGES - 1 k-steps in flight instead of one register-staged step; two CTAs per SM.
+// The band reduction's Y = C22 V (N = 32) is a STREAM of C22 (8 flops per byte: 1.8 TB/s register-staged, 6.8 ->
+// 4.9 ms with this kernel); the rank-64 .. rank-256 updates of the Cholesky, the triangular solves and the band
+// reduction run 16 k-steps or fewer per tile, where the load latency of every step was exposed.
+constexpr int AS_LDA = BK + 4;                                   // pitch of [rows][BK] tiles (== 4 mod 16)
+template <int TB, int BN> struct AsyncCfg {
+  static constexpr int LDB = TB ? BK + 4 : BN + 4;
+  static constexpr int B_DOUBLES = TB ? BN * (BK + 4) : BK * (BN + 4);
+  static constexpr int STAGE = BM * AS_LDA + B_DOUBLES;
+  static constexpr int STAGES = BN == 32 ? 4 : 3;
+  static constexpr int SMEM = STAGES * STAGE * (int)sizeof(double);
+};
 
 __device__ __forceinline__ void cp_async16(double* dst, const double* src, int bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) gemm_skinny_kernel(GemmArgs g) {
+template <int TB, int BN>
+__global__ void __launch_bounds__(256, 2) gemm_async_kernel(GemmArgs g) {
+  using Cfg = AsyncCfg<TB, BN>;
+  constexpr int WN = BN / 32, WM = 8 / WN, WR = BM / WM, RT = WR / 8;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(16) double smem[];
-  const int m0 = blockIdx.y * BM;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.tri && n0 > m0 + BM - 1) return;
   const int nsp = g.split > 1 ? g.split : 1;
   const int zb = blockIdx.z / nsp, zs = blockIdx.z % nsp;
   const double* __restrict__ A = g.A + (size_t)zb * g.strideA + (size_t)zs * g.splitA;
@@ -186,82 +196,113 @@ __global__ void __launch_bounds__(256, 2) gemm_skinny_kernel(GemmArgs g) {
   double* __restrict__ C = g.C + (size_t)zb * g.strideC + (size_t)zs * g.splitC;
   const int K = g.split_ktot > 0 ? max(0, min(g.K, g.split_ktot - zs * g.K)) : g.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp * 16, gq = lane >> 2, tq = lane & 3;
+  const int wm = (warp / WN) * WR, wn = (warp % WN) * 32;
+  const int gq = lane >> 2, tq = lane & 3;
   const int nk = (K + BK - 1) / BK;
 
   auto issue = [&](int kt) {
-    double* as = smem + (size_t)(kt % SK_STAGES) * SK_STAGE_DOUBLES;
-    double* bs = as + BM * SK_LDA;
+    double* as = smem + (size_t)(kt % STAGES) * Cfg::STAGE;
+    double* bs = as + BM * AS_LDA;
     const int k0 = kt * BK;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {           // A tile: 128 rows x 8 chunks of 2 doubles
       const int c = tid + 256 * u, row = c >> 3, col = k0 + 2 * (c & 7);
       const bool ok = m0 + row < g.M && col < K;
-      const int bytes = ok ? min(16, (K - col) * 8) : 0;
-      cp_async16(as + row * SK_LDA + 2 * (c & 7), ok ? A + (size_t)(m0 + row) * g.lda + col : A, bytes);
+      cp_async16(as + row * AS_LDA + 2 * (c & 7), ok ? A + (size_t)(m0 + row) * g.lda + col : A,
+                 ok ? min(16, (K - col) * 8) : 0);
     }
-    {                                        // B tile: 16 rows x 16 chunks
-      const int krow = tid >> 4, col = 2 * (tid & 15);
-      const bool ok = k0 + krow < K && col < g.N;
-      const int bytes = ok ? min(16, (g.N - col) * 8) : 0;
-      cp_async16(bs + krow * SK_LDB + col, ok ? B + (size_t)(k0 + krow) * g.ldb + col : B, bytes);
+    if (TB) {                                // B stored N x K: BN rows x 8 chunks
+#pragma unroll
+      for (int u = 0; u < BN / 32; ++u) {
+        const int c = tid + 256 * u, row = c >> 3, col = k0 + 2 * (c & 7);
+        const bool ok = n0 + row < g.N && col < K;
+        cp_async16(bs + row * Cfg::LDB + 2 * (c & 7), ok ? B + (size_t)(n0 + row) * g.ldb + col : B,
+                   ok ? min(16, (K - col) * 8) : 0);
+      }
+    } else {                                 // B stored K x N: 16 rows x BN / 2 chunks
+#pragma unroll
+      for (int u = 0; u < BN / 32; ++u) {
+        const int c = tid + 256 * u, krow = c / (BN / 2), col = 2 * (c % (BN / 2));
+        const bool ok = k0 + krow < K && n0 + col < g.N;
+        cp_async16(bs + krow * Cfg::LDB + col, ok ? B + (size_t)(k0 + krow) * g.ldb + n0 + col : B,
+                   ok ? min(16, (g.N - n0 - col) * 8) : 0);
+      }
     }
   };
 
-  double acc[2][4][2];
+  double acc[RT][4][2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int s = 0; s < SK_STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) issue(s);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int kt = 0; kt < nk; ++kt) {
-    asm volatile("cp.async.wait_group %0;" ::"n"(SK_STAGES - 2) : "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
     __syncthreads();
-    if (kt + SK_STAGES - 1 < nk) issue(kt + SK_STAGES - 1);
+    if (kt + STAGES - 1 < nk) issue(kt + STAGES - 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const double* a_s = smem + (size_t)(kt % SK_STAGES) * SK_STAGE_DOUBLES;
-    const double* b_s = a_s + BM * SK_LDA;
+    const double* a_s = smem + (size_t)(kt % STAGES) * Cfg::STAGE;
+    const double* b_s = a_s + BM * AS_LDA;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[2], b[4];
+      double a[RT], b[4];
 #pragma unroll
-      for (int rt = 0; rt < 2; ++rt) a[rt] = a_s[(wm + rt * 8 + gq) * SK_LDA + kk * 4 + tq];
+      for (int rt = 0; rt < RT; ++rt) a[rt] = a_s[(wm + rt * 8 + gq) * AS_LDA + kk * 4 + tq];
 #pragma unroll
-      for (int ct = 0; ct < 4; ++ct) b[ct] = b_s[(kk * 4 + tq) * SK_LDB + ct * 8 + gq];
+      for (int ct = 0; ct < 4; ++ct)
+        b[ct] = TB ? b_s[(wn + ct * 8 + gq) * Cfg::LDB + kk * 4 + tq] : b_s[(kk * 4 + tq) * Cfg::LDB + wn + ct * 8 + gq];
 #pragma unroll
-      for (int rt = 0; rt < 2; ++rt)
+      for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
         for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+  const bool vecC = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  const bool mir = g.tri && g.mirror && m0 >= n0 + BN;
 #pragma unroll
-  for (int rt = 0; rt < 2; ++rt) {
+  for (int rt = 0; rt < RT; ++rt) {
     const int r = m0 + wm + rt * 8 + gq;
     if (r >= g.M) continue;
 #pragma unroll
     for (int ct = 0; ct < 4; ++ct) {
-      const int c = ct * 8 + 2 * tq;
+      const int c = n0 + wn + ct * 8 + 2 * tq;
       double* p = C + (size_t)r * g.ldc + c;
-      const double v0 = g.alpha * acc[rt][ct][0], v1 = g.alpha * acc[rt][ct][1];
-      if (c < g.N) p[0] = v0 + (g.beta != 0.0 ? g.beta * p[0] : 0.0);
-      if (c + 1 < g.N) p[1] = v1 + (g.beta != 0.0 ? g.beta * p[1] : 0.0);
+      double v0 = g.alpha * acc[rt][ct][0], v1 = g.alpha * acc[rt][ct][1];
+      if (c + 1 < g.N && vecC) {
+        if (g.beta != 0.0) {
+          double2 o = *reinterpret_cast<double2*>(p);
+          v0 += g.beta * o.x;
+          v1 += g.beta * o.y;
+        }
+        *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+      } else {
+        if (c < g.N) p[0] = v0 = v0 + (g.beta != 0.0 ? g.beta * p[0] : 0.0);
+        if (c + 1 < g.N) p[1] = v1 = v1 + (g.beta != 0.0 ? g.beta * p[1] : 0.0);
+      }
+      if (mir) {
+        if (c < g.N) C[(size_t)c * g.ldc + r] = v0;
+        if (c + 1 < g.N) C[(size_t)(c + 1) * g.ldc + r] = v1;
+      }
     }
   }
 }
 
-int launch_skinny(const GemmArgs& g, cudaStream_t st) {
+template <int TB, int BN>
+int launch_async(const GemmArgs& g, cudaStream_t st) {
+  using Cfg = AsyncCfg<TB, BN>;
   static thread_local bool configured = false;
   if (!configured) {
-    APV_CUDA_TRY(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    APV_CUDA_TRY(cudaFuncSetAttribute(gemm_async_kernel<TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  dim3 grid(1, ceil_div(g.M, BM), (g.batch > 0 ? g.batch : 1) * (g.split > 1 ? g.split : 1));
-  gemm_skinny_kernel<<<grid, 256, SK_SMEM_BYTES, st>>>(g);
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), (g.batch > 0 ? g.batch : 1) * (g.split > 1 ? g.split : 1));
+  gemm_async_kernel<TB, BN><<<grid, 256, Cfg::SMEM, st>>>(g);
   APV_CUDA_TRY(cudaGetLastError());
   return OK;
 }
@@ -293,11 +334,15 @@ int launch(const GemmArgs& g, cudaStream_t st) {
 
 int gemm_f64(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return OK;
-  // streaming skinny product: 16-byte aligned rows of A and B (cp.async), any M, N <= 32, K
-  if (!g.transA && !g.transB && !g.tri && g.N <= SK_BN && g.K >= 4 * BK && (g.lda & 1) == 0 && (g.ldb & 1) == 0 &&
+  // cp.async tiles: op(A) = A with 16-byte aligned rows of both operands, the 128 x 64 / 128 x 32 tile range
+  static const bool no_async = getenv("APV_GEMM_NO_ASYNC") != nullptr;
+  const bool tile64 = g.N <= 64 || g.bn == 64 || (g.bn == 0 && g.K <= 1024);
+  if (!no_async && !g.transA && tile64 && g.K >= 2 * BK && (g.lda & 1) == 0 && (g.ldb & 1) == 0 &&
       (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 &&
-      (g.strideA & 1) == 0 && (g.strideB & 1) == 0 && (g.splitA & 1) == 0 && (g.splitB & 1) == 0)
-    return launch_skinny(g, st);
+      (g.strideA & 1) == 0 && (g.strideB & 1) == 0 && (g.splitA & 1) == 0 && (g.splitB & 1) == 0) {
+    if (g.N <= 32) return g.transB ? launch_async<1, 32>(g, st) : launch_async<0, 32>(g, st);
+    return g.transB ? launch_async<1, 64>(g, st) : launch_async<0, 64>(g, st);
+  }
   if (g.transA) return g.transB ? launch<1, 1>(g, st) : launch<1, 0>(g, st);
   return g.transB ? launch<0, 1>(g, st) : launch<0, 0>(g, st);
 }
