@@ -23,6 +23,7 @@ struct JdiagWs {
   double* Tm = nullptr;     // [nz][n][ldn]  scratch (transpose)
   double* VH = nullptr;     // [nz][n][ldn]  Householder vectors, row j = v_j
   double* Dinv = nullptr;   // [nz][n/nb][nb][nb] inverses of the Cholesky diagonal blocks
+  double* SBinv = nullptr;  // [nz][n/256][256][256] inverses of the diagonal super-blocks (triangular solves)
   double* Z1 = nullptr;     // [nz][n][2 nbt]  [V | W] panel
   double* Z2 = nullptr;     // [nz][n][2 nbt]  [W | V] panel
   double* tau = nullptr;    // [nz][n]

@@ -215,6 +215,97 @@ __global__ void __launch_bounds__(128) chol_diag_kernel(double* __restrict__ Lm,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Inverses of the SB x SB diagonal blocks of the Cholesky factor, assembled from the NB x NB diagonal-block inverses
+// (Dinv) by the block recurrence  X_ii = Dinv_i,  X_ij = -Dinv_i sum_{k=j..i-1} L_ik X_kj  (i > j).  With them a
+// triangular solve is ONE product per super-block plus ONE trailing update (the NB-block substitution inside a
+// super-block needed eight small launches).  grid (n / SB, nz), 256 threads (4 x 4 outputs each), 96 KB smem.
+__global__ void __launch_bounds__(256) sb_inv_kernel(const double* __restrict__ Lm, const double* __restrict__ Dinv,
+                                                     double* __restrict__ SBinv, int n, int ldn, int nblk) {
+  extern __shared__ double si_sm[];
+  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(si_sm);
+  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(si_sm + NB * (NB + 1));
+  double (*Cs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(si_sm + 2 * NB * (NB + 1));
+  const int sb = blockIdx.x, z = blockIdx.y, tid = threadIdx.x;
+  const int s0 = sb * SB;
+  const double* L = Lm + (size_t)z * n * ldn;
+  const double* Di = Dinv + (size_t)z * nblk * NB * NB;
+  double* X = SBinv + ((size_t)z * gridDim.x + sb) * SB * SB;          // [SB][SB] row-major
+  const int ty = tid >> 4, tx = tid & 15;                                // outputs rows 4 ty.., cols 4 tx..
+  constexpr int Q = SB / NB;
+  // zero above the diagonal blocks, diagonal blocks from Dinv
+  for (int i = tid; i < SB * SB; i += 256) {
+    const int r = i / SB, c = i % SB, bi = r / NB, bj = c / NB;
+    double v = 0.0;
+    if (bi == bj && sb * Q + bi < nblk) v = Di[((size_t)(sb * Q + bi) * NB + (r % NB)) * NB + (c % NB)];
+    X[i] = v;
+  }
+  __syncthreads();
+  auto load_tile = [&](double (*T)[NB + 1], const double* src, int ld, int rows_valid, int cols_valid) {
+    for (int i = tid; i < NB * NB; i += 256) {
+      const int r = i / NB, c = i % NB;
+      T[r][c] = (r < rows_valid && c < cols_valid) ? src[(size_t)r * ld + c] : 0.0;
+    }
+  };
+  for (int i = 1; i < Q; ++i) {
+    if (s0 + i * NB >= n) break;
+    for (int j = i - 1; j >= 0; --j) {
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int k = j; k < i; ++k) {            // acc += L_ik X_kj
+        __syncthreads();
+        load_tile(As, L + (size_t)(s0 + i * NB) * ldn + s0 + k * NB, ldn, min(NB, n - s0 - i * NB), NB);
+        load_tile(Bs, X + (size_t)(k * NB) * SB + j * NB, SB, NB, NB);
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < NB; ++q) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) av[a] = As[4 * ty + a][q];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) bv[b] = Bs[q][4 * tx + b];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Cs[4 * ty + a][4 * tx + b] = acc[a][b];
+      load_tile(As, Di + (size_t)(sb * Q + i) * NB * NB, NB, NB, NB);      // Dinv_i
+      __syncthreads();
+      double out[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) out[a][b] = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < NB; ++q) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = As[4 * ty + a][q];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = Cs[q][4 * tx + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) out[a][b] = fma(av[a], bv[b], out[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) X[(size_t)(i * NB + 4 * ty + a) * SB + j * NB + 4 * tx + b] = -out[a][b];
+      __threadfence_block();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // out = in^T (per zone), 32x32 tiles.
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int n, int ldn) {
   __shared__ double t[32][33];
@@ -1001,6 +1092,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.Tm, mat));
   APV_TRY(al((void**)&ws.VH, mat));
   APV_TRY(al((void**)&ws.Dinv, (size_t)nz * nblk * NB * NB * sizeof(double)));
+  APV_TRY(al((void**)&ws.SBinv, (size_t)nz * ceil_div(n, SB) * SB * SB * sizeof(double)));
   APV_TRY(al((void**)&ws.Z1, (size_t)nz * n * 2 * NBT * sizeof(double)));
   APV_TRY(al((void**)&ws.Z2, (size_t)nz * n * 2 * NBT * sizeof(double)));
   const size_t vec = (size_t)nz * n * sizeof(double);
@@ -1035,7 +1127,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
@@ -1051,46 +1143,31 @@ void jdiag_free(JdiagWs& ws) {
   ws = JdiagWs();
 }
 
-// X <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones.
-// X <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones.
-// Blocked forward substitution with delayed updates: inside a super-block of NSUB x NB rows the NB-row blocks are
-// solved with the precomputed diagonal-block inverses and rank-NB updates confined to the super-block; everything
-// below receives ONE rank-(NSUB NB) DMMA update, so the right-hand side is streamed n / (NSUB NB) times only.
-static int trsm_lower(JdiagWs& ws, double* X, int m, int ldx, long long strideX, cudaStream_t st, int* launches) {
-  const int n = ws.n, ldn = ws.ldn, nblk = ceil_div(n, NB);
+// Y <- L^-1 X for an n x m right-hand side (row-major, leading dimension ldx), batched over zones; X is destroyed.
+// Blocked forward substitution on super-blocks of SB rows: Y_s = Linv_ss X_s with the explicit inverse of the
+// diagonal super-block (sb_inv_kernel), then ONE rank-SB DMMA update of everything below, so the right-hand side
+// is streamed n / SB times and there are two launches per super-block.
+static int trsm_lower(JdiagWs& ws, double* X, double* Y, int m, int ldx, long long strideX, cudaStream_t st,
+                      int* launches) {
+  const int n = ws.n, ldn = ws.ldn, nsb = ceil_div(n, SB);
   const long long mstride = (long long)n * ldn;
   for (int s0 = 0; s0 < n; s0 += SB) {
-    const int s1 = std::min(n, s0 + SB);
-    for (int k0 = s0; k0 < s1; k0 += NB) {
-      const int nbk = std::min(NB, n - k0);
-      GemmArgs g{};
-      g.batch = ws.nz;
-      // X_k <- Linv_kk X_k (in place: one row tile, each CTA owns its columns)
-      g.A = ws.Dinv + (size_t)(k0 / NB) * NB * NB; g.lda = NB; g.strideA = (long long)nblk * NB * NB;
-      g.B = X + (size_t)k0 * ldx; g.ldb = ldx; g.strideB = strideX;
-      g.C = X + (size_t)k0 * ldx; g.ldc = ldx; g.strideC = strideX;
-      g.M = nbk; g.N = m; g.K = nbk; g.alpha = 1.0; g.beta = 0.0;
-      APV_TRY(gemm_f64(g, st));
-      ++*launches;
-      const int rem = s1 - k0 - nbk;            // rows of the super-block still to be solved
-      if (rem > 0) {
-        GemmArgs u{};
-        u.batch = ws.nz;
-        u.A = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; u.lda = ldn; u.strideA = mstride;
-        u.B = X + (size_t)k0 * ldx; u.ldb = ldx; u.strideB = strideX;
-        u.C = X + (size_t)(k0 + nbk) * ldx; u.ldc = ldx; u.strideC = strideX;
-        u.M = rem; u.N = m; u.K = nbk; u.alpha = -1.0; u.beta = 1.0;
-        APV_TRY(gemm_f64(u, st));
-        ++*launches;
-      }
-    }
+    const int s1 = std::min(n, s0 + SB), rows = s1 - s0;
+    GemmArgs g{};
+    g.batch = ws.nz;
+    g.A = ws.SBinv + (size_t)(s0 / SB) * SB * SB; g.lda = SB; g.strideA = (long long)nsb * SB * SB;
+    g.B = X + (size_t)s0 * ldx; g.ldb = ldx; g.strideB = strideX;
+    g.C = Y + (size_t)s0 * ldx; g.ldc = ldx; g.strideC = strideX;
+    g.M = rows; g.N = m; g.K = rows; g.alpha = 1.0; g.beta = 0.0;
+    APV_TRY(gemm_f64(g, st));
+    ++*launches;
     if (s1 < n) {
       GemmArgs u{};
       u.batch = ws.nz;
       u.A = ws.Lm + (size_t)s1 * ldn + s0; u.lda = ldn; u.strideA = mstride;
-      u.B = X + (size_t)s0 * ldx; u.ldb = ldx; u.strideB = strideX;
+      u.B = Y + (size_t)s0 * ldx; u.ldb = ldx; u.strideB = strideX;
       u.C = X + (size_t)s1 * ldx; u.ldc = ldx; u.strideC = strideX;
-      u.M = n - s1; u.N = m; u.K = s1 - s0; u.alpha = -1.0; u.beta = 1.0;
+      u.M = n - s1; u.N = m; u.K = rows; u.alpha = -1.0; u.beta = 1.0;
       APV_TRY(gemm_f64(u, st));
       ++*launches;
     }
@@ -1157,11 +1234,17 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
 
   APV_CUDA_TRY(cudaEventRecord(ws.ev[1], st));
   // ---- C = L^-1 A L^-T, symmetrised
-  APV_TRY(trsm_lower(ws, ws.Cm, n, ldn, mstride, st, &nl));
+  {
+    const size_t sism = (size_t)3 * NB * (NB + 1) * sizeof(double);
+    APV_TRY(ensure_smem(sb_inv_kernel, sism));
+    sb_inv_kernel<<<dim3(ceil_div(n, SB), nz), 256, sism, st>>>(ws.Lm, ws.Dinv, ws.SBinv, n, ldn, nblk);
+    ++nl;
+  }
+  APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = L^-1 A
   dim3 tb(32, 8), tg(ceil_div(n, 32), ceil_div(n, 32), nz);
-  transpose_kernel<<<tg, tb, 0, st>>>(ws.Cm, ws.Tm, n, ldn);
+  transpose_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);                // Cm = A L^-T
   ++nl;
-  APV_TRY(trsm_lower(ws, ws.Tm, n, ldn, mstride, st, &nl));
+  APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = L^-1 A L^-T
   symmetrize_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);
   ++nl;
 
