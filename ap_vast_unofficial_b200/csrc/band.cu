@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(Q2W_T, 1) sb2st_apply_q2_wave_kernel(SbQ2 a) {
 // T and updates its rows.  (One CTA per vector re-read every panel from L2: 17 GB of L2 traffic at n = 4096.)
 // Cooperative launch, grid = (n / Q1RS) CTAs per zone, 512 threads.
 constexpr int Q1T = 512;
-constexpr int Q1RS = 256;        // rows per CTA
+constexpr int Q1RS = 128;        // rows per CTA (n = 8192, two zones: 128 CTAs, all co-resident)
 constexpr int Q1VC = 64;         // vectors per chunk
 constexpr int Q1VP = NB2 + 2;    // pitch of the staged reflector rows (even: 16-byte loads, conflict-free)
 
