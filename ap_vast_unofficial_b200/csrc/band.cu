@@ -100,8 +100,13 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
     cluster.sync();
     SB_TICK(3);
     if (warp == 0) {           // reflector scalars once per CTA (32 warps doing this redundantly fill the FP64 pipe)
-      double g = 0.0;
-      for (int k = 0; k < CS; ++k) g += xpart[par][k][lane];
+      double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < QR_MAXCS; k += 2) {          // (unrolled: the loads of all ranks' partials are in flight together)
+        if (k < CS) g0 += xpart[par][k][lane];
+        if (k + 1 < CS) g1 += xpart[par][k + 1][lane];
+      }
+      const double g = g0 + g1;
       const double rowj = (j < npn) ? xrow[par][lane] : 0.0;      // (no diagonal row: the column is empty)
       const double alpha = __shfl_sync(0xffffffffu, rowj, j), sigma = __shfl_sync(0xffffffffu, g, j);
       double beta = alpha, tau = 0.0, scale = 0.0;
