@@ -103,3 +103,25 @@ def test_sharded_two_ranks_emulated_matches_single_stream():
         assert np.linalg.norm(outs[t] - ref["out_A"][t]) <= 1e-8 * np.linalg.norm(ref["out_A"][t]), t
         for v in range(ws[t].shape[0]):
             assert np.linalg.norm(ws[t][v] - ref["w_A"][t][v]) <= 1e-8 * np.linalg.norm(ref["w_A"][t][v]), (t, v)
+
+
+def test_render_signal_equals_the_per_hop_loop():
+    """io.render_signal = the driver loop of make_python_test.m:44-54 on a whole signal."""
+    from ap_vast_unofficial_b200 import apvast
+    from ap_vast_unofficial_b200 import io as apio
+    rng = np.random.default_rng(21)
+    K, L, M = 32, 3, 2
+    rA = 1e-3 * rng.standard_normal((K, L, M)); rB = 1e-3 * rng.standard_normal((K, L, M))
+    cfg = dict(block_size=64, filter_length=8, modeling_delay=2, reference_index_A=0, reference_index_B=1,
+               number_of_eigenvectors=5, mu=1.0, statistics_buffer_length=96, perceptual=False)
+    x, y = rng.standard_normal(32 * 7 + 5), rng.standard_normal(32 * 7)
+    np.random.seed(2); e1 = apvast(rir_A=rA, rir_B=rB, **cfg)
+    fa, fb, wA, wB = apio.render_signal(e1, x, y, rank=3, collect_filters=True)
+    np.random.seed(2); e2 = apvast(rir_A=rA, rir_B=rB, **cfg)
+    ref = []
+    for a, b in apio.hop_blocks(x, y, 32):
+        oA, oB, _, _ = e2.process_input_buffers(a, b)
+        ref.append(np.array(oA[2]))
+    assert fa.shape == (8 * 32, L) and fb.shape == (8 * 32, L) and wA.shape == (8, L * 8)
+    assert np.array_equal(fa, np.concatenate(ref, axis=0))
+    assert np.array_equal(wA[-1], np.array(e2.w_A[2]).reshape(-1))
