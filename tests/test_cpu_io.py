@@ -64,3 +64,16 @@ def test_render_signal_against_a_stub_engine():
     assert np.array_equal(fa[:10, 0], 2 * x) and np.array_equal(fa[:10, 1], 4 * x) and np.all(fa[10:] == 0)
     with pytest.raises(ValueError):
         apio.render_signal(Stub(), x, x, rank=4)
+
+
+def test_static_statistics_match_the_vast_m_loops():
+    """static_design.static_statistics (vectorised) against the loop restatement of vast.m:42-75."""
+    from ap_vast_unofficial_b200.static_design import static_statistics
+    from oracle.vast_static_oracle import vast_oracle
+    rng = np.random.default_rng(4)
+    M, I, L, J, delay, ref = 3, 17, 2, 5, 2, 1
+    gB, gD = rng.standard_normal((M, I, L)), rng.standard_normal((M, I, L))
+    for N in (40, 12):                       # 12 < I: the reference's fixed horizon truncates the responses
+        RB, RD, rB = static_statistics(gB, gD, J, delay, ref, n_samples=N)
+        _, RBo, RDo, rBo = vast_oracle(gB, gD, J, delay, ref, 1, 1.0, N=N)
+        assert np.max(np.abs(RB - RBo)) < 1e-13 and np.max(np.abs(RD - RDo)) < 1e-13 and np.max(np.abs(rB - rBo)) < 1e-13

@@ -125,3 +125,18 @@ def test_render_signal_equals_the_per_hop_loop():
     assert fa.shape == (8 * 32, L) and fb.shape == (8 * 32, L) and wA.shape == (8, L * 8)
     assert np.array_equal(fa, np.concatenate(ref, axis=0))
     assert np.array_equal(wA[-1], np.array(e2.w_A[2]).reshape(-1))
+
+
+@pytest.mark.parametrize("V", [1, 7, 24])
+def test_static_vast_design_against_the_vast_m_restatement(V):
+    """static_design.vast_static (host statistics + apv_jdiag on the GPU) against oracle/vast_static_oracle.py."""
+    from ap_vast_unofficial_b200.static_design import vast_static
+    from oracle.vast_static_oracle import vast_oracle
+    rng = np.random.default_rng(11)
+    M, I, L, J = 4, 40, 3, 8
+    dec = np.exp(-np.arange(I) / 10.0)[None, :, None]
+    gB, gD = rng.standard_normal((M, I, L)) * dec, rng.standard_normal((M, I, L)) * dec
+    w = vast_static(gB, gD, J, 3, 1, V, 0.8)
+    wo, _, _, _ = vast_oracle(gB, gD, J, 3, 1, V, 0.8)
+    assert w.shape == (J, L)
+    assert np.linalg.norm(w - wo) / np.linalg.norm(wo) < 1e-8
