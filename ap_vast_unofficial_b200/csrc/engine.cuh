@@ -33,7 +33,6 @@ struct JdiagWs {
   double* ybuf = nullptr;   // [nz][n]
   double* wbuf = nullptr;   // [nz][n]
   double* tdws = nullptr;   // scratch of the tridiagonalisation panel kernel (partials, tile partial vectors)
-  double* vcur = nullptr;   // (unused)
   double* Tf = nullptr;     // [nz][n/8][8][8] compact-WY T factors of the reflector blocks
   double* lam = nullptr;    // [nz][V]   top-V eigenvalues, descending
   double* shift = nullptr;  // [nz][V]   perturbed shifts for inverse iteration

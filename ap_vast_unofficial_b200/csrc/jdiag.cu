@@ -1,10 +1,12 @@
 // S5  jdiag -- joint diagonalisation of (R_B, R_D) (reference jdiag, Python/apvast.py:20-36;
 // spec Matlab/ControlMethods/jdiag.m:103-116):
 //     Bc = chol(R_D + reg I)             -> chol_f64   (blocked right-looking, DMMA trailing update)
-//     C  = Bc^-1 R_B Bc^-T               -> trsm_f64   (blocked, diagonal-block inverses + DMMA GEMM)
-//     C  = Q Lambda Q^T                  -> syevd_f64  (blocked Householder tridiagonalisation, then
-//                                           top-V eigenpairs of T by multisection bisection and
-//                                           inverse iteration, back-transformed by the reflectors)
+//     C  = Bc^-1 R_B Bc^-T               -> trsm_f64   (blocked, inverses of the diagonal super-blocks + DMMA GEMM)
+//     C  = Q Lambda Q^T                  -> syevd_f64  (tridiagonalisation: two stages for n >= 1024 (band.cu: DMMA
+//                                           band reduction + bulge chasing), one blocked Householder stage below
+//                                           (tridiag.cu), shared-memory Jacobi for n <= 48; then top-V eigenpairs
+//                                           of T by multisection and inverse iteration, back-transformed by the
+//                                           reflectors)
 //     U  = Bc^-T Q, columns sorted by descending eigenvalue
 // The reference calls a non-symmetric real Schur (LAPACK dgees) on a matrix that is symmetric to
 // rounding; here C is symmetrised and a symmetric eigensolver is used.  Only the V leading pairs
@@ -1103,7 +1105,6 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
   APV_TRY(al((void**)&ws.ybuf, vec));
   APV_TRY(al((void**)&ws.wbuf, vec));
   APV_TRY(al((void**)&ws.tdws, tridiag_scratch_doubles(n, nz) * sizeof(double)));
-  APV_TRY(al((void**)&ws.vcur, (size_t)nz * 2 * n * sizeof(double)));
   APV_TRY(al((void**)&ws.Tf, (size_t)nz * ceil_div(n, WYB) * WYB * WYB * sizeof(double)));
   APV_TRY(al((void**)&ws.lam, (size_t)nz * V * sizeof(double)));
   APV_TRY(al((void**)&ws.shift, (size_t)nz * V * sizeof(double) + (size_t)nz * 4 * sizeof(double)));
@@ -1127,7 +1128,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.vcur, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
