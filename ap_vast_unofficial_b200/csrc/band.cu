@@ -110,9 +110,10 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       const double rowj = (j < npn) ? xrow[par][lane] : 0.0;      // (no diagonal row: the column is empty)
       const double alpha = __shfl_sync(0xffffffffu, rowj, j), sigma = __shfl_sync(0xffffffffu, g, j);
       double beta = alpha, tau = 0.0, scale = 0.0;
-      if (sigma > 0.0 && j < npn - 1) {
-        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-        tau = (beta - alpha) / beta;
+      if (sigma > 0.0 && j < npn - 1) {      // (as warp_house below: one rsqrt and one reciprocal)
+        const double nrm2 = fma(alpha, alpha, sigma), r = rsqrt(nrm2);
+        beta = -copysign(nrm2 * r, alpha);
+        tau = fma(fabs(alpha), r, 1.0);
         scale = 1.0 / (alpha - beta);
       }
       const double q = fma(scale, g, rowj);     // lane > j: (v^T P)[lane];  lane < j: (V^T V)[lane][j]
@@ -452,8 +453,11 @@ __device__ __forceinline__ void warp_house(double x, int lane, double& v, double
   if (ss == 0.0) {
     beta = alpha; tau = 0.0; v = (lane == 0) ? 1.0 : 0.0;
   } else {
-    beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-    tau = (beta - alpha) / beta;
+    // one reciprocal square root and one reciprocal instead of a square root and two divisions (this chain sits on
+    // the critical path of every chase step):  |beta| = nrm2 r,  tau = (beta - alpha) / beta = 1 + |alpha| r
+    const double nrm2 = fma(alpha, alpha, ss), r = rsqrt(nrm2);
+    beta = -copysign(nrm2 * r, alpha);
+    tau = fma(fabs(alpha), r, 1.0);
     v = (lane == 0) ? 1.0 : x * (1.0 / (alpha - beta));
   }
 }
