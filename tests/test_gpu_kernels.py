@@ -53,7 +53,10 @@ def _spd_pair(n, rng, cols=3):
                                           # eig_mode 3 = two-stage (band reduction + bulge chasing); 24: band only,
                                           # 34: the smallest panel, 65 / 97: partial last blocks
                                           (24, 24, 3), (34, 10, 3), (65, 65, 3), (97, 20, 3), (100, 100, 3),
-                                          (257, 33, 3), (640, 64, 3), (1100, 64, 3)])
+                                          (257, 33, 3), (640, 64, 3), (1100, 64, 3),
+                                          # V = 100: four 32-vector groups in the wavefront back-transformation;
+                                          # V = 150: the per-vector back-transformation kernel
+                                          (700, 100, 3), (300, 150, 3)])
 def test_jdiag_identities_and_filters(n, V, eig_mode):
     """jdiag.m:33-35 identities and the filter sum against the reference route (oracle jdiag)."""
     from ap_vast_unofficial_b200 import jdiag
