@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(Q2T) sb2st_apply_q2_kernel(double* __restrict_
 
 
 // ------------------------------------------------------------------------------------------------
-// Z <- Q2 Z, wavefront form for a handful of eigenvectors (V <= Q2W_MAXV): lane = eigenvector, so a reflector is
+// Z <- Q2 Z, wavefront form: lane = eigenvector (groups of 32 vectors are independent problems), so a reflector is
 // applied with thread-local dot products -- no shuffles, no CTA barriers.  A warp owns a CHAIN: the 32 consecutive
 // sweeps [S, S+32) for 32 vectors, and walks down the band in blocks k = 0, 1, ..: block k applies the reflectors
 // (s, k), s = S+31 .. S, which act on the rows [S+1+32k, S+64+32k) -- a window of 63 rows per lane in registers
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(Q2T) sb2st_apply_q2_kernel(double* __restrict_
 // acquire block counters, like the rows of the bulge chasing.  The reflectors of a block (32 x 32 doubles) are
 // staged in shared memory and read as broadcasts.  Cooperative launch, 128 threads, one chain per warp.
 constexpr int Q2W_T = 128;
-constexpr int Q2W_MAXV = 128;
+constexpr int Q2W_MAXV = 8192;
 
 struct SbQ2 {
   double* iv; const double* V2; int* prog;
@@ -1236,7 +1236,7 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
   const bool dbg = getenv("APV_TS_DEBUG") != nullptr;
   if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   if (ws.V <= Q2W_MAXV && !getenv("APV_Q2_PER_VECTOR")) {
-    // few vectors: wavefront of chains, lane = vector (the per-vector kernel pays a CTA barrier per sweep)
+    // wavefront of chains, lane = vector (the per-vector kernel below pays a CTA barrier per sweep; APV_Q2_PER_VECTOR=1)
     SbQ2 q;
     q.iv = ws.iv; q.V2 = ws.Tm; q.n = n; q.ldn = ws.ldn; q.Vp = ws.Vp; q.nz = ws.nz;
     q.ngrp = ceil_div(n - 2, NB2); q.nhalf = ws.Vp / 32;

@@ -54,8 +54,7 @@ def _spd_pair(n, rng, cols=3):
                                           # 34: the smallest panel, 65 / 97: partial last blocks
                                           (24, 24, 3), (34, 10, 3), (65, 65, 3), (97, 20, 3), (100, 100, 3),
                                           (257, 33, 3), (640, 64, 3), (1100, 64, 3),
-                                          # V = 100: four 32-vector groups in the wavefront back-transformation;
-                                          # V = 150: the per-vector back-transformation kernel
+                                          # V = 100 / 150: four / five 32-vector groups in the wavefront back-transformation
                                           (700, 100, 3), (300, 150, 3)])
 def test_jdiag_identities_and_filters(n, V, eig_mode):
     """jdiag.m:33-35 identities and the filter sum against the reference route (oracle jdiag)."""
