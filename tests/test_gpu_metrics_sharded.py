@@ -3,6 +3,8 @@
 import numpy as np
 import pytest
 
+from tests._golden import rel
+
 pytestmark = pytest.mark.gpu
 
 
@@ -140,3 +142,37 @@ def test_static_vast_design_against_the_vast_m_restatement(V):
     wo, _, _, _ = vast_oracle(gB, gD, J, 3, 1, V, 0.8)
     assert w.shape == (J, L)
     assert np.linalg.norm(w - wo) / np.linalg.norm(wo) < 1e-8
+
+
+@pytest.mark.parametrize("Z", [2, 3, 4])
+def test_multizone_engine_against_the_oracle_generalisation(Z):
+    """zones.apvast_zones (one two-zone engine per bright zone, dark zone = union of the other zones' microphones)
+    against oracle/multizone_oracle.py (pairwise two-zone oracles + explicit sums): BASELINE cfg-5 semantics."""
+    from ap_vast_unofficial_b200.zones import apvast_zones
+    from oracle.multizone_oracle import MultiZoneOracle
+    rng = np.random.default_rng(30 + Z)
+    K, L, M, J, V = 24, 3, 2, 6, 6
+    dec = np.exp(-np.arange(K) / 6.0).reshape(-1, 1, 1)
+    rirs = [1e-3 * rng.standard_normal((K, L, M)) * dec for _ in range(Z)]
+    refs = [z % L for z in range(Z)]
+    cfg = dict(block_size=32, filter_length=J, modeling_delay=2, number_of_eigenvectors=V, mu=0.5,
+               statistics_buffer_length=48)
+    np.random.seed(1)
+    gpu = apvast_zones(rirs=rirs, reference_indices=refs, **cfg)
+    ora = MultiZoneOracle(rirs=rirs, reference_indices=refs, seed=1, **cfg)
+    for t in range(10):                       # the random start buffers are flushed after (Nb + N) / H + 2 hops
+        xs = [rng.standard_normal(16) for _ in range(Z)]
+        outs = gpu.process_input_buffers(xs)
+        ora.process_input_buffers(xs)
+    assert len(outs) == Z and len(outs[0]) == V and outs[0][0].shape == (16, L)
+    for z in range(Z):
+        RB, RD, rB = gpu.statistics(z)
+        assert rel(RB, ora.R_B[z]) < 1e-11 and rel(RD, ora.R_D[z]) < 1e-11 and rel(rB[:, 0], ora.r_B[z]) < 1e-11
+        lam = gpu.eigenvalues[z]
+        assert np.max(np.abs(lam - ora.lam[z][:V])) / ora.lam[z][0] < 1e-10
+        w = gpu.w[z][:, :, 0]
+        gap = np.abs(np.diff(ora.lam[z][:V + 1])) / ora.lam[z][0]
+        for v in range(V):
+            if gap[v] > 1e-9:
+                assert rel(w[v], ora.w[z][v]) < 1e-8, (z, v)
+    gpu.close()

@@ -86,3 +86,25 @@ def test_matlab_flavour_closed_form():
     # target of zone B sits on loudspeaker reference_index_B
     ft = eng.filter_spectra_B_t[0]
     assert np.allclose(np.abs(ft[:, 2]), 1.0) and np.allclose(ft[:, 0], 0.0)
+
+
+def test_multizone_oracle_reduces_to_the_two_zone_oracle():
+    """oracle/multizone_oracle.py (SURVEY 8d cfg-5 generalisation) at Z = 2 is the pinned two-zone oracle."""
+    from oracle.apvast_oracle import ApvastOracle
+    from oracle.multizone_oracle import MultiZoneOracle
+    rng = np.random.default_rng(5)
+    K, L, M, J, V = 24, 2, 2, 6, 5
+    rirs = [1e-3 * rng.standard_normal((K, L, M)) for _ in range(2)]
+    cfg = dict(block_size=32, filter_length=J, modeling_delay=2, number_of_eigenvectors=V, mu=0.5,
+               statistics_buffer_length=48)
+    mz = MultiZoneOracle(rirs=rirs, reference_indices=[0, 1], seed=3, **cfg)
+    np.random.seed(3)
+    two = ApvastOracle(rir_A=rirs[0], rir_B=rirs[1], reference_index_A=0, reference_index_B=1, perceptual=False, **cfg)
+    for t in range(6):
+        a, b = rng.standard_normal(16), rng.standard_normal(16)
+        mz.process_input_buffers([a, b])
+        two.process_input_buffers(a, b)
+    for v in range(V):
+        wa, wb = np.array(two.w_A)[v, :, 0], np.array(two.w_B)[v, :, 0]
+        assert np.linalg.norm(mz.w[0][v] - wa) / np.linalg.norm(wa) < 1e-9
+        assert np.linalg.norm(mz.w[1][v] - wb) / np.linalg.norm(wb) < 1e-9
