@@ -32,6 +32,7 @@ class Config(C.Structure):
         ("mu", C.c_double), ("reg", C.c_double), ("sampling_rate", C.c_double),
         ("toeplitz_clean", C.c_int32), ("normalize_stats", C.c_int32), ("loading_mode", C.c_int32),
         ("target_ref_per_zone", C.c_int32), ("bright_load", C.c_double), ("dark_load", C.c_double),
+        ("active_mics_A", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -68,7 +68,7 @@ class apvast:
                  statistics_buffer_length: int, hop_size: int = None, sampling_rate: int = 48000,
                  run_A: bool = True, run_B: bool = True, perceptual: bool = True, *, model=None,
                  device: int = None, eig_mode: int = 0, stats_mode: int = 0, flavour: str = "python",
-                 fullscale_db: float = 94.0):
+                 fullscale_db: float = 94.0, active_mics_A: int = 0):
         self._h = None
         if flavour not in ("python", "matlab"):
             raise RuntimeError("flavour must be 'python' or 'matlab'")
@@ -143,7 +143,8 @@ class apvast:
             eig_mode=int(eig_mode),
             stats_mode=int(stats_mode), device=-1 if device is None else int(device), mu=self._mu, reg=1e-7,
             sampling_rate=float(sampling_rate), toeplitz_clean=int(matlab), normalize_stats=int(matlab),
-            loading_mode=int(matlab), target_ref_per_zone=int(matlab), bright_load=1e-8, dark_load=5e-3)
+            loading_mode=int(matlab), target_ref_per_zone=int(matlab), bright_load=1e-8, dark_load=5e-3,
+            active_mics_A=int(active_mics_A), reserved0=0)
         h = C.c_void_p()
         capi.check(capi.lib().apv_create(C.byref(cfg), capi.ptr(rA), capi.ptr(rB), capi.ptr(init), C.byref(h)))
         self._h = h

@@ -478,10 +478,22 @@ int stage_stats(Handle& h) {
   }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[0], h.st));
   int nl = 0;
+  // paths into zone A (0: A->A, 2: B->A) stop at the last real microphone of zone A (silent padding microphones of
+  // the multi-zone composition contribute nothing); groups of four microphones
+  const int MA = (h.cfg.active_mics_A > 0 && h.cfg.active_mics_A < D.M) ? round_up(h.cfg.active_mics_A, 4) : D.M;
   for (int m0 = 0; m0 < D.M; m0 += 4) {
     const int mc = std::min(4, D.M - m0);
-    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, pmask, m0, mc);
-    syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, pmask, mc, m0 == 0, m0 + 4 >= D.M);
+    const unsigned mA = m0 < MA ? (pmask & 0x5u) : 0u, mB = pmask & 0xAu;
+    if ((mA | mB) == 0u) continue;
+    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc);
+    const bool lastA = m0 + 4 >= MA, lastB = m0 + 4 >= D.M;
+    if (mA && mB && lastA != lastB) {
+      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mA, mc, m0 == 0, lastA);
+      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mB, mc, m0 == 0, lastB);
+      ++nl;
+    } else {
+      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mA | mB, mc, m0 == 0, mA ? lastA : lastB);
+    }
     nl += 2;
   }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));

@@ -7,8 +7,8 @@ engine.  The reference (``Python/apvast.py``) has exactly two zones; the general
 followed by the same joint diagonalisation and rank-V filter sum.  Because R_{z -> z'} is a sum over the microphones of
 zone z' (``apvast.py:332-364`` loops over m), R_D(z) is exactly the cross-zone matrix of a TWO-zone problem whose
 second zone holds the microphones of all the other zones.  One two-zone engine per bright zone therefore does the
-whole job on the GPU, unchanged: zone A = zone z (padded with silent microphones to the common count), zone B = the
-union of the other zones, ``run_B=False``.  The loudspeaker signal of the array is the sum of the zones' feeds.
+whole job on the GPU, unchanged: zone A = zone z (padded with silent microphones to the common count, which the
+statistics skip: ``active_mics_A``), zone B = the union of the other zones, ``run_B=False``.  The loudspeaker signal of the array is the sum of the zones' feeds.
 
 Per-zone perceptual weighting (each dark microphone weighted from its own zone's target) needs one target signal per
 microphone group and is not expressible in this composition: ``perceptual=False`` only.
@@ -44,7 +44,7 @@ class apvast_zones:
             dark = np.concatenate([rirs[q] for q in range(Z) if q != z], axis=2)
             self.engines.append(apvast(block_size, bright, dark, filter_length, modeling_delay, reference_indices[z], 0,
                                        number_of_eigenvectors, mu, statistics_buffer_length, hop_size, sampling_rate,
-                                       run_A=True, run_B=False, perceptual=False, **engine_kwargs))
+                                       run_A=True, run_B=False, perceptual=False, active_mics_A=M, **engine_kwargs))
         self.hop_size = self.engines[0].hop_size
         self._silence = np.zeros(self.hop_size)
 

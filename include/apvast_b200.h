@@ -71,6 +71,10 @@ typedef struct apv_config {
   int32_t target_ref_per_zone; /* 1: target of zone B uses reference_index_B (apVast.m:597-600)     */
   double bright_load;        /* brightCondLimit, MATLAB 1e-8 (apVast.m:560)                         */
   double dark_load;          /* darkCondLimit, MATLAB 5e-3 (apVast.m:559)                           */
+  /* more than two zones by composition (zones.py): the microphones m >= active_mics_A of zone A are silent padding
+     (zero RIRs) and are skipped by the statistics; 0 = all n_mics are real */
+  int32_t active_mics_A;
+  int32_t reserved0;
 } apv_config;
 
 typedef struct apv_handle apv_handle;

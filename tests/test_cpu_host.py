@@ -33,7 +33,7 @@ def test_config_struct_layout_matches_header():
         if m:
             names += [x.strip() for x in m.group(2).split(",")]
     assert names == [f[0] for f in _capi.Config._fields_]
-    assert C.sizeof(_capi.Config) == 18 * 4 + 3 * 8 + 4 * 4 + 2 * 8
+    assert C.sizeof(_capi.Config) == 18 * 4 + 3 * 8 + 4 * 4 + 2 * 8 + 2 * 4
 
 
 def test_library_links_no_vendor_math_libraries():
