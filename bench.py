@@ -356,9 +356,9 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
                     "share_of_step": kt_syrk / (dev_ms_max / K) if dev_ms_max > 0 else None,
                     "traffic": 1.029e9 * 4,
-                    "traffic_source": "profiles/r01_ncu_full_v2.txt (ncu --set full, one of the 4 launches per block: "
-                                      "6.8 MB read + 1.02 GB written)",
-                    "ncu_tensor_pipe_pct": 90.5}
+                    "traffic_source": "profiles/r01_ncu_full_v3.txt (ncu --set full, one of the 4 launches per block: "
+                                      "7.7 MB read + 1.02 GB written -- the per-microphone partial matrices)",
+                    "ncu_tensor_pipe_pct": 94.4}
         if two_stage:
             td_flops = 2.0 * 4.0 * n ** 3 / 3.0           # 4 n^3 / 3 per zone
             td_ms = float(stage_acc.get("S5_tridiag", 0.0))
