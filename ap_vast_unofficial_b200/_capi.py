@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libapvast_b200.so")
 
 # status codes (enum apv_status)
-OK, EINVAL, ENOTPD, ECUDA, ENOMEM, ENOCONV = range(6)
+OK, EINVAL, ENOTPD, ECUDA, ENOMEM, ENOCONV, ENCCL = range(7)
 
 # tensor ids (enum apv_tensor)
 (T_W, T_LAMBDA, T_U, T_R, T_RVEC, T_WEIGHT, T_RESP, T_RESP_T, T_OLA, T_OLA_T, T_STATS, T_STATS_T,
@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("mu", C.c_double), ("reg", C.c_double), ("sampling_rate", C.c_double),
         ("toeplitz_clean", C.c_int32), ("normalize_stats", C.c_int32), ("loading_mode", C.c_int32),
         ("target_ref_per_zone", C.c_int32), ("bright_load", C.c_double), ("dark_load", C.c_double),
-        ("active_mics_A", C.c_int32), ("reserved0", C.c_int32),
+        ("active_mics_A", C.c_int32), ("reg_relative", C.c_int32),
     ]
 
 
@@ -50,6 +50,22 @@ SIGNATURES = {
     "apv_begin_block": (C.c_int, [C.c_void_p, _dp, _dp]),
     "apv_finish_block": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "apv_advance_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "apv_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "apv_set_reg_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "apv_copy_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "apv_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "apv_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "apv_comm_destroy": (C.c_int, [C.c_void_p]),
+    "apv_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "apv_range_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "apv_range_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "apv_range_exchange_halo": (C.c_int, [C.c_void_p]),
+    "apv_range_gather": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
+    "apv_range_device_ptrs": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4),
+    "apv_range_tail_get": (C.c_int, [C.c_void_p, _dp]),
+    "apv_range_tail_add": (C.c_int, [C.c_void_p, _dp]),
+    "apv_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "apv_free_pinned": (None, [C.c_void_p]),
     "apv_get": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
     "apv_set": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_size_t]),
     "apv_set_mu": (C.c_int, [C.c_void_p, C.c_double]),
@@ -98,6 +114,27 @@ def ptr(a):
         return None
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_dp)
+
+
+def pinned_array(shape):
+    """float64 NumPy array in page-locked host memory (cudaMallocHost): the destination of asynchronous D2H copies."""
+    n = int(np.prod(shape))
+    p = lib().apv_alloc_pinned(max(n, 1) * 8)
+    if not p:
+        raise MemoryError(last_error())
+    buf = (C.c_double * max(n, 1)).from_address(p)
+    a = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+    _PINNED[a.__array_interface__["data"][0]] = p
+    return a
+
+
+def free_pinned(a):
+    p = _PINNED.pop(a.__array_interface__["data"][0], None)
+    if p:
+        lib().apv_free_pinned(p)
+
+
+_PINNED = {}
 
 
 def last_error() -> str:

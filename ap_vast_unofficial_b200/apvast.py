@@ -101,8 +101,6 @@ class apvast:
             raise RuntimeError("block size must be modulo 2")
         if np.shape(rir_A) != np.shape(rir_B):
             raise RuntimeError("rirs of unequal size")
-        if not EXPERIMENTAL_REGULARIZATION:
-            raise NotImplementedError("only the reference default EXPERIMENTAL_REGULARIZATION=True (reg=1e-7) is built")
 
         rA = np.ascontiguousarray(rir_A, dtype=np.float64)
         rB = np.ascontiguousarray(rir_B, dtype=np.float64)
@@ -144,7 +142,7 @@ class apvast:
             stats_mode=int(stats_mode), device=-1 if device is None else int(device), mu=self._mu, reg=1e-7,
             sampling_rate=float(sampling_rate), toeplitz_clean=int(matlab), normalize_stats=int(matlab),
             loading_mode=int(matlab), target_ref_per_zone=int(matlab), bright_load=1e-8, dark_load=5e-3,
-            active_mics_A=int(active_mics_A), reserved0=0)
+            active_mics_A=int(active_mics_A), reg_relative=int(not EXPERIMENTAL_REGULARIZATION))
         h = C.c_void_p()
         capi.check(capi.lib().apv_create(C.byref(cfg), capi.ptr(rA), capi.ptr(rB), capi.ptr(init), C.byref(h)))
         self._h = h
@@ -154,6 +152,14 @@ class apvast:
         self._mode = mode
         self._n = self.filter_length * L
         self._blocks = 0
+        self._reg_relative = not EXPERIMENTAL_REGULARIZATION
+
+    def _sync_flags(self):
+        # the reference reads EXPERIMENTAL_REGULARIZATION inside jdiag, i.e. at call time (Python/apvast.py:22-27)
+        rel = not EXPERIMENTAL_REGULARIZATION
+        if rel != self._reg_relative:
+            capi.check(capi.lib().apv_set_reg_mode(self._h, int(rel)))
+            self._reg_relative = rel
 
     # ------------------------------------------------------------------ life-cycle
     def close(self):
@@ -190,6 +196,7 @@ class apvast:
         oAt = np.empty((H, L))
         oBt = np.empty((H, L))
         lib = capi.lib()
+        self._sync_flags()
         if self._mode == 2:
             capi.check(lib.apv_begin_block(self._h, capi.ptr(a), capi.ptr(b)))
             self._host_gains()
@@ -218,6 +225,40 @@ class apvast:
                     g = g / np.linalg.norm(g)
                 W[z, m] = g
         self._set(capi.T_WEIGHT, W)
+
+    def process_blocks(self, signal_A, signal_B, want_filters=False):
+        """Throughput form of the per-hop loop (``make_python_test.m:44-54``): ``nblocks`` consecutive hops in ONE call,
+        results identical to ``nblocks`` calls of ``process_input_buffers``.  S1-S4 of hop t+1 overlap S5-S7 of hop t
+        on the device and the rendered hops are copied out asynchronously.
+
+        Returns ``(out_A, out_B, out_A_t, out_B_t[, w])``: arrays (nblocks, V, H, L) (``None`` for a zone that is off),
+        (nblocks, H, L) for the target streams, and with ``want_filters`` the per-hop filters (nblocks, 2, V, n)."""
+        if self._mode == 2:
+            raise RuntimeError("process_blocks is not available with a host perceptual model")
+        a = np.ascontiguousarray(signal_A, dtype=np.float64).reshape(-1)
+        b = np.ascontiguousarray(signal_B, dtype=np.float64).reshape(-1)
+        H = self.hop_size
+        if a.size != b.size or a.size % H != 0:
+            raise RuntimeError("invalid input size")
+        nb = a.size // H
+        V, L = self.number_of_eigenvectors, self.number_of_srcs
+        oA = np.empty((nb, V, H, L)) if self.run_A else None
+        oB = np.empty((nb, V, H, L)) if self.run_B else None
+        oAt, oBt = np.empty((nb, H, L)), np.empty((nb, H, L))
+        w = np.empty((nb, 2, V, self._n)) if want_filters else None
+        self._sync_flags()
+        capi.check(capi.lib().apv_process_blocks(self._h, nb, capi.ptr(a), capi.ptr(b), capi.ptr(oA), capi.ptr(oB),
+                                                 capi.ptr(oAt), capi.ptr(oBt), capi.ptr(w)))
+        self._blocks += nb
+        if self._ranks is not None:
+            sel = [r - 1 for r in self._ranks]
+            oA = oA[:, sel] if oA is not None else None
+            oB = oB[:, sel] if oB is not None else None
+        return (oA, oB, oAt, oBt, w) if want_filters else (oA, oB, oAt, oBt)
+
+    def set_pipeline(self, on: bool):
+        """Overlap of S1-S4 of hop t+1 with S5-S7 of hop t in multi-hop calls (default on; results are identical)."""
+        capi.check(capi.lib().apv_set_pipeline(self._h, int(bool(on))))
 
     def advance_state(self, input_A, input_B):
         """S1-S3 only (state update without statistics/filters/rendering): warm-up of a block range."""

@@ -1067,7 +1067,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     p.Cm = ws.Cm; p.VH = ws.VH; p.VP = VP; p.tau = ws.tau; p.Tp = Tp + (size_t)(j0 / NB2) * nz * NB2 * NB2;
     p.n = n; p.ldn = ldn; p.j0 = j0; p.rows_per = ceil_div(npn, CS); p.dbg = dbg.on ? dclk : nullptr;
     const size_t smem = (size_t)p.rows_per * PP * sizeof(double);
-    static thread_local size_t configured = 0;
+    static PerDevice pd_configured; size_t& configured = pd_configured.cur();
     if (smem > configured) {
       APV_CUDA_TRY(cudaFuncSetAttribute(sb_panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)std::max(smem, (size_t)(184 * 1024))));
@@ -1116,7 +1116,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     sb_w1_kernel<<<dim3(w.nblk, nz), 256, 0, st>>>(w);
     {
       const size_t w2smem = (size_t)(3 * NB2 + 2 * 64) * PP * sizeof(double);
-      static thread_local bool w2cfg = false;
+      static PerDevice pd_w2cfg; size_t& w2cfg = pd_w2cfg.cur();
       if (!w2cfg) {
         APV_CUDA_TRY(cudaFuncSetAttribute(sb_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w2smem));
         w2cfg = true;
@@ -1186,7 +1186,7 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       const int want = ceil_div(n / NB2 + 2 * CGW, 2 * CGW + 1) + 4;
       const int G = std::max(1, std::min(std::min(sms / nz, want), ngroups));
       const size_t smem = (size_t)CG_NSLOT * CG_PITCH * sizeof(double);
-      static thread_local bool configured = false;
+      static PerDevice pd_configured; size_t& configured = pd_configured.cur();
       if (!configured) {
         APV_CUDA_TRY(cudaFuncSetAttribute(sb2st_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -1227,7 +1227,7 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
     return EINVAL_;
   }
   const size_t smem = (size_t)n * sizeof(double);
-  static thread_local size_t configured = 0;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (smem > 48 * 1024 && smem > configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(sb2st_apply_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -1280,7 +1280,7 @@ int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches) {
   q.bar = reinterpret_cast<unsigned long long*>(q.Sp + (size_t)nz * 2 * G * NB2 * Q1VC);
   q.n = n; q.ldn = ws.ldn; q.V = ws.V; q.Vp = ws.Vp; q.nz = nz; q.npanels = npanels;
   const size_t smem = (size_t)(Q1RS * Q1VC + Q1RS * Q1VP + NB2 * Q1VC) * sizeof(double);
-  static thread_local bool configured = false;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (!configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(sb_apply_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

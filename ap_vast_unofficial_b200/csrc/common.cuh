@@ -8,7 +8,7 @@ namespace apv {
 
 // ----------------------------------------------------------------------------------------------
 // status codes (mirrored in include/apvast_b200.h)
-enum { OK = 0, EINVAL_ = 1, ENOTPD = 2, ECUDA = 3, ENOMEM_ = 4, ENOCONV = 5 };
+enum { OK = 0, EINVAL_ = 1, ENOTPD = 2, ECUDA = 3, ENOMEM_ = 4, ENOCONV = 5, ENCCL = 6 };
 
 #define APV_CUDA_TRY(expr)                                                                     \
   do {                                                                                         \
@@ -27,6 +27,16 @@ enum { OK = 0, EINVAL_ = 1, ENOTPD = 2, ECUDA = 3, ENOMEM_ = 4, ENOCONV = 5 };
   } while (0)
 
 extern thread_local char g_err[512];
+
+// cudaFuncSetAttribute belongs to the device context, not to the calling thread: bookkeeping per device ordinal.
+struct PerDevice {
+  size_t v[64] = {};
+  size_t& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -11,8 +11,7 @@
 
 using namespace apv;
 
-namespace {
-
+namespace apv {
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -20,6 +19,9 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+}  // namespace apv
+
+namespace {
 
 template <typename T>
 int dalloc(T** p, size_t count) {
@@ -98,7 +100,8 @@ int run_jdiag(Handle& h) {
     dark[zi] = h.R + (zone == 0 ? 1 : 2) * ms;
   }
   if (h.nz == 1) { bright[1] = bright[0]; dark[1] = dark[0]; }
-  return jdiag_run(h.jd, bright, dark, D.ldn, h.cfg.loading_mode == 1 ? 0.0 : h.cfg.reg, h.st, &h.launches);
+  return jdiag_run(h.jd, bright, dark, D.ldn, h.cfg.loading_mode == 1 ? 0.0 : h.cfg.reg, h.st, &h.launches,
+                   (h.cfg.reg_relative && h.cfg.loading_mode != 1) ? h.regv : nullptr);
 }
 
 int check_info(Handle& h) {
@@ -117,30 +120,62 @@ int check_info(Handle& h) {
   return OK;
 }
 
-// S1..S7 with the inputs already on the device.  `from_targets`: S1 was already run (split call).
-int run_block(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only) {
+void use_slot(Handle& h, int slot) {
+  h.R = h.Rslot[slot];
+  h.rvec = h.rvslot[slot];
+  h.xw = h.xwslot[slot];
+}
+
+}  // namespace
+
+namespace apv {
+
+// Front half of a block: S1-S3 (state) and S4 (statistics into the current slot), on the stream h.st points at.
+// `skip_s1`: S1 was already run (split call).  `state_only`: warm-up of a block range, no statistics.
+int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only) {
   cudaEvent_t* ev = h.ev;
-  h.launches = 0;
   APV_CUDA_TRY(cudaEventRecord(ev[0], h.st));
   if (!skip_s1) APV_TRY(stage_fir(h, d_inA, d_inB));
   APV_CUDA_TRY(cudaEventRecord(ev[1], h.st));
-  APV_TRY(stage_targets(h, false));
+  if (!(skip_s1 && h.cfg.perceptual == 3)) APV_TRY(stage_targets(h, false));   // 3: S2 ran in apv_begin_block
   APV_TRY(stage_weighted(h));
   APV_CUDA_TRY(cudaEventRecord(ev[2], h.st));
   if (!state_only) {
     APV_TRY(stage_stats(h));
     if (h.cfg.loading_mode == 1) APV_TRY(stage_loading(h));
-    APV_CUDA_TRY(cudaEventRecord(ev[3], h.st));
-    APV_TRY(run_jdiag(h));
-    APV_TRY(publish_eig(h));
-    APV_CUDA_TRY(cudaEventRecord(ev[4], h.st));
-    APV_TRY(stage_sweep(h, h.cfg.mu, h.W));
-    APV_CUDA_TRY(cudaEventRecord(ev[5], h.st));
-    APV_TRY(stage_render(h));
-  } else {
-    for (int i = 3; i <= 5; ++i) APV_CUDA_TRY(cudaEventRecord(ev[i], h.st));
+    else if (h.cfg.reg_relative && h.nz > 0) APV_TRY(stage_spectral_norms(h));
   }
+  APV_CUDA_TRY(cudaEventRecord(ev[3], h.st));
+  return OK;
+}
+
+// Back half: S5 (joint diagonalisation of the current slot), S6 (filter sum into h.W), S7 (rendering into h.d_out).
+int run_back(Handle& h) {
+  cudaEvent_t* ev = h.ev;
+  APV_CUDA_TRY(cudaEventRecord(ev[7], h.st));
+  APV_TRY(run_jdiag(h));
+  APV_TRY(publish_eig(h));
+  APV_CUDA_TRY(cudaEventRecord(ev[4], h.st));
+  APV_TRY(stage_sweep(h, h.cfg.mu, h.W));
+  APV_CUDA_TRY(cudaEventRecord(ev[5], h.st));
+  APV_TRY(stage_render(h));
   APV_CUDA_TRY(cudaEventRecord(ev[6], h.st));
+  return OK;
+}
+
+}  // namespace apv
+
+namespace {
+
+// S1..S7 in order on the main stream with the inputs already on the device (the per-block call).
+int run_block(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only) {
+  h.launches = 0;
+  APV_TRY(run_front(h, d_inA, d_inB, skip_s1, state_only));
+  if (!state_only) {
+    APV_TRY(run_back(h));
+  } else {
+    for (int i : {7, 4, 5, 6}) APV_CUDA_TRY(cudaEventRecord(h.ev[i], h.st));
+  }
   return OK;
 }
 
@@ -174,6 +209,104 @@ int copy_out(Handle& h, double* out_A, double* out_B, double* out_A_t, double* o
     memset(o, 0, (size_t)D.H * D.L * sizeof(double));
     for (int i = 0; i < D.H; ++i) o[(size_t)i * D.L + lt] = t[(size_t)X * D.H + i];
   }
+  return OK;
+}
+
+}  // namespace
+
+namespace apv {
+
+bool pipelined(const Handle& h) {
+  // the MATLAB loading and the norm-relative regularisation read spectral norms back to the host inside S4
+  return h.pipeline != 0 && h.cfg.loading_mode != 1 && !h.cfg.reg_relative && h.cfg.perceptual < 2;
+}
+
+// One block of a multi-block call.  With pipelining the front half (S1-S4) goes to the low-priority stream and fills
+// slot b & 1 of the statistics while the back half (S5-S7) of block b - 1 still runs on the main stream: S4 of
+// block b + 1 depends on the streaming state only (apvast.py:329-364), never on the filters of block b.
+// `b` counts from 0 inside the call; results are written to the device buffers of `sink`.
+int enqueue_block(Handle& h, long b, const double* d_inA, const double* d_inB, const BlockSink& sink, bool state_only) {
+  const int slot = (int)(b & 1);
+  const bool pipe = pipelined(h) && !state_only;
+  cudaStream_t main_st = h.st;
+  h.launches = 0;
+  use_slot(h, slot);
+  if (pipe) {
+    if (b >= 2) {
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[slot], 0));     // back half of block b - 2 released the slot
+    } else if (b == 0) {
+      APV_CUDA_TRY(cudaEventRecord(h.ev_free[1], main_st));                  // state written by earlier calls
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[1], 0));
+    }
+    h.st = h.st_front;
+  }
+  int rc = run_front(h, d_inA, d_inB, false, state_only);
+  h.st = main_st;
+  APV_TRY(rc);
+  if (state_only) {
+    for (int i : {7, 4, 5, 6}) APV_CUDA_TRY(cudaEventRecord(h.ev[i], h.st));
+    return OK;
+  }
+  if (pipe) {
+    APV_CUDA_TRY(cudaEventRecord(h.ev_ready[slot], h.st_front));
+    APV_CUDA_TRY(cudaStreamWaitEvent(main_st, h.ev_ready[slot], 0));
+  }
+  h.W = sink.W ? sink.W : h.home_W;
+  h.d_out = sink.out ? sink.out : h.home_out;
+  h.d_out_t = sink.out_t ? sink.out_t : h.home_out_t;
+  rc = run_back(h);
+  if (rc == OK && sink.info && h.nz > 0)
+    rc = cudaMemcpyAsync(sink.info, h.jd.info, (size_t)h.nz * 4 * sizeof(int), cudaMemcpyDeviceToDevice, main_st) == cudaSuccess
+             ? OK : fail(ECUDA, "status copy failed");
+  if (rc == OK && pipe) rc = cudaEventRecord(h.ev_free[slot], main_st) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
+  return rc;
+}
+
+// after a multi-block call: the filters / outputs of the last block back into the handle's own buffers, so that
+// apv_get and the next per-block call see the usual layout
+int leave_multiblock(Handle& h) {
+  const Dims& D = h.D;
+  if (h.W != h.home_W)
+    APV_CUDA_TRY(cudaMemcpyAsync(h.home_W, h.W, 2 * (size_t)D.V * D.n * sizeof(double), cudaMemcpyDeviceToDevice, h.st));
+  if (h.d_out != h.home_out)
+    APV_CUDA_TRY(cudaMemcpyAsync(h.home_out, h.d_out, 2 * (size_t)D.V * D.H * D.L * sizeof(double), cudaMemcpyDeviceToDevice, h.st));
+  if (h.d_out_t != h.home_out_t)
+    APV_CUDA_TRY(cudaMemcpyAsync(h.home_out_t, h.d_out_t, 2 * (size_t)D.H * sizeof(double), cudaMemcpyDeviceToDevice, h.st));
+  h.W = h.home_W; h.d_out = h.home_out; h.d_out_t = h.home_out_t;
+  return OK;
+}
+
+int status_from_info(const Handle& h, const int* info, long block) {
+  for (int zi = 0; zi < h.nz; ++zi) {
+    if (info[zi * 4] != 0)
+      return fail(ENOTPD, "Matrix is not positive definite (block %ld, zone %c, pivot %d)", block,
+                  h.zones[zi] == 0 ? 'A' : 'B', info[zi * 4]);
+    if (info[zi * 4 + 1] != 0)
+      return fail(ENOCONV, "eigen-solver did not converge (block %ld, zone %c, flags %d)", block,
+                  h.zones[zi] == 0 ? 'A' : 'B', info[zi * 4 + 1]);
+  }
+  return OK;
+}
+
+}  // namespace apv
+
+namespace {
+
+size_t ring_slot_doubles(const Dims& D) {
+  return 2 * (size_t)D.V * D.H * D.L + 2 * (size_t)D.H + 2 * (size_t)D.V * D.n + 8;   // out | out_t | W | status
+}
+
+int ensure_ring(Handle& h, int cap) {
+  if (h.ring_cap >= cap) return OK;
+  if (h.ring) cudaFree(h.ring);
+  if (h.ring_pin) cudaFreeHost(h.ring_pin);
+  h.ring = h.ring_pin = nullptr;
+  h.ring_cap = h.ring_pin_cap = 0;
+  const size_t sd = ring_slot_doubles(h.D);
+  APV_CUDA_TRY(cudaMalloc((void**)&h.ring, (size_t)cap * sd * sizeof(double)));
+  APV_CUDA_TRY(cudaMemsetAsync(h.ring, 0, (size_t)cap * sd * sizeof(double), h.st));
+  APV_CUDA_TRY(cudaMallocHost((void**)&h.ring_pin, (size_t)cap * sd * sizeof(double)));
+  h.ring_cap = h.ring_pin_cap = cap;
   return OK;
 }
 
@@ -224,17 +357,32 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   if (h->cfg.dark_load <= 0) h->cfg.dark_load = 5e-3;
   h->D = D;
   auto bail = [&](int code) { apv_destroy(h); return code; };
-  if (cfg->device >= 0) {
-    if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(ECUDA, "cudaSetDevice(%d) failed", cfg->device));
-  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return bail(fail(ECUDA, "no CUDA device: the AP-VAST B200 engine has no CPU fallback"));
-  cudaGetDevice(&h->device);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  h->device = cfg->device >= 0 ? cfg->device : cur;
+  if (h->device >= ndev) return bail(fail(ECUDA, "cudaSetDevice(%d) failed: %d device(s) visible", h->device, ndev));
+  DevGuard dg(h->device);      // everything below, and every later call on the handle, runs on the handle's device
 #define TRYB(x) do { int _s = (x); if (_s != OK) return bail(_s); } while (0)
 #define CUB(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return bail(fail(ECUDA, "%s -> %s", #x, cudaGetErrorString(_e))); } while (0)
-  CUB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;      // numerically lowest value = highest priority
+    CUB(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUB(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
+    CUB(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));
+    CUB(cudaStreamCreateWithPriority(&h->st_copy, cudaStreamNonBlocking, hi));
+  }
   for (auto& e : h->ev) CUB(cudaEventCreate(&e));
+  for (auto& e : h->ev_ready) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_free) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_rend) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_d2h) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  {
+    const char* pe = getenv("APV_PIPELINE");
+    h->pipeline = pe ? atoi(pe) : 1;
+  }
   for (auto& e : h->ev_syrk) CUB(cudaEventCreate(&e));
   for (auto& e : h->ev_timer) CUB(cudaEventCreate(&e));
   const size_t K = D.K, L = D.L, M = D.M, Nb = D.Nb, N = D.N, V = D.V, n = D.n;
@@ -258,14 +406,20 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
   TRYB(dalloc(&h->G, 2 * V * L * Nb));
   TRYB(dalloc(&h->Gt, 2 * Nb));
-  TRYB(dalloc(&h->R, 4 * n * (size_t)D.ldn));
-  TRYB(dalloc(&h->rvec, 2 * n));
+  for (int s = 0; s < 2; ++s) {
+    TRYB(dalloc(&h->Rslot[s], 4 * n * (size_t)D.ldn));
+    TRYB(dalloc(&h->rvslot[s], 2 * n));
+    TRYB(dalloc(&h->xwslot[s], 2 * Nb));
+  }
+  h->R = h->Rslot[0]; h->rvec = h->rvslot[0]; h->xw = h->xwslot[0];
+  TRYB(dalloc(&h->regv, 2));
   TRYB(dalloc(&h->lam, 2 * V));
   TRYB(dalloc(&h->U, 2 * V * n));
-  TRYB(dalloc(&h->W, 2 * V * n));
+  TRYB(dalloc(&h->home_W, 2 * V * n));
   TRYB(dalloc(&h->d_in, 2 * (size_t)D.H));
-  TRYB(dalloc(&h->d_out, 2 * V * (size_t)D.H * L));
-  TRYB(dalloc(&h->d_out_t, 2 * (size_t)D.H));
+  TRYB(dalloc(&h->home_out, 2 * V * (size_t)D.H * L));
+  TRYB(dalloc(&h->home_out_t, 2 * (size_t)D.H));
+  h->W = h->home_W; h->d_out = h->home_out; h->d_out_t = h->home_out_t;
   h->nz = 0;
   if (D.runA) h->zones[h->nz++] = 0;
   if (D.runB) h->zones[h->nz++] = 1;
@@ -302,18 +456,21 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
     CUB(cudaMemcpy(h->rirTT, tt.data(), tt.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (init_resp) {  // 4 x (Nb, L, M) then 2 x (Nb, M)  ->  [path][m][l][t], [zone][m][t]
+    // silent padding microphones of zone A (active_mics_A, multi-zone composition) do not exist: their start buffers
+    // stay zero, whatever the statistics kernels sum over
+    const size_t MA = (cfg->active_mics_A > 0 && cfg->active_mics_A < D.M) ? (size_t)cfg->active_mics_A : M;
     buf.assign(4 * M * L * Nb, 0.0);
     for (size_t p = 0; p < 4; ++p)
       for (size_t t = 0; t < Nb; ++t)
         for (size_t l = 0; l < L; ++l)
-          for (size_t m = 0; m < M; ++m)
+          for (size_t m = 0; m < ((p & 1) == 0 ? MA : M); ++m)       // paths 0 (A->A) and 2 (B->A) end in zone A
             buf[((p * M + m) * L + l) * Nb + t] = init_resp[p * Nb * L * M + (t * L + l) * M + m];
     CUB(cudaMemcpy(h->Q, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
     const double* tr = init_resp + 4 * Nb * L * M;
     buf.assign(2 * M * Nb, 0.0);
     for (size_t X = 0; X < 2; ++X)
       for (size_t t = 0; t < Nb; ++t)
-        for (size_t m = 0; m < M; ++m) buf[(X * M + m) * Nb + t] = tr[X * Nb * M + t * M + m];
+        for (size_t m = 0; m < (X == 0 ? MA : M); ++m) buf[(X * M + m) * Nb + t] = tr[X * Nb * M + t * M + m];
     CUB(cudaMemcpy(h->QT, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   fill_kernel<<<64, 256, 0, h->st>>>(h->Wg, 2 * M * (size_t)D.F, 1.0);   // W == 1 (apvast.py:326-327)
@@ -326,13 +483,29 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
 
 void apv_destroy(apv_handle* h) {
   if (!h) return;
+  DevGuard dg(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->st_front) cudaStreamSynchronize(h->st_front);
+  if (h->st_copy) cudaStreamSynchronize(h->st_copy);
+  range_free(*h);
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
-                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->R, h->rvec, h->lam, h->U, h->W, h->d_in, h->d_out,
-                h->d_out_t};
+                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->Rslot[0], h->Rslot[1],
+                h->rvslot[0], h->rvslot[1], h->xwslot[0], h->xwslot[1], h->regv, h->lam, h->U, h->home_W, h->d_in,
+                h->home_out, h->home_out_t, h->ring};
   for (void* p : ps)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->ring_pin) cudaFreeHost(h->ring_pin);
+  if (h->ring_info) cudaFreeHost(h->ring_info);
   jdiag_free(h->jd);
+  for (cudaEvent_t* arr : {h->ev_ready, h->ev_free})
+    for (int i = 0; i < 2; ++i)
+      if (arr[i]) cudaEventDestroy(arr[i]);
+  for (cudaEvent_t* arr : {h->ev_rend, h->ev_d2h})
+    for (int i = 0; i < 4; ++i)
+      if (arr[i]) cudaEventDestroy(arr[i]);
+  if (h->st_front) cudaStreamDestroy(h->st_front);
+  if (h->st_copy) cudaStreamDestroy(h->st_copy);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_syrk)
@@ -347,39 +520,99 @@ int apv_process_block(apv_handle* h, const double* in_A, const double* in_B, dou
                       double* out_A_t, double* out_B_t) {
   if (!h || !in_A || !in_B) return fail(EINVAL_, "null argument");
   if (h->cfg.perceptual == 1 && !h->G2) return fail(EINVAL_, "perceptual model tables not set (apv_set_gain_table)");
-  if (h->cfg.perceptual == 2) return fail(EINVAL_, "perceptual == 2 needs apv_begin_block / apv_finish_block");
+  if (h->cfg.perceptual >= 2) return fail(EINVAL_, "this perceptual mode needs apv_begin_block / apv_finish_block");
+  DevGuard dg(h->device);
   APV_TRY(copy_in(*h, in_A, in_B));
   APV_TRY(run_block(*h, h->d_in, h->d_in + h->D.H, false, false));
   APV_TRY(copy_out(*h, out_A, out_B, out_A_t, out_B_t));
   return check_info(*h);
 }
 
+// Throughput path.  The hops are copied to the device once; block b + 1's S1-S4 overlap block b's S5-S7 on a second
+// stream (two statistics slots); every block is rendered into a ring slot in HBM, copied to a pinned host ring on a
+// copy stream and handed to the caller one block behind, so nothing on the device waits for the host.
 int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const double* in_B, double* out_A,
                        double* out_B, double* out_A_t, double* out_B_t, double* w_out) {
-  if (!h || nblocks < 0) return fail(EINVAL_, "bad argument");
+  if (!h || nblocks < 0 || (nblocks > 0 && (!in_A || !in_B))) return fail(EINVAL_, "bad argument");
+  if (h->cfg.perceptual == 1 && !h->G2) return fail(EINVAL_, "perceptual model tables not set (apv_set_gain_table)");
+  if (h->cfg.perceptual >= 2) return fail(EINVAL_, "this perceptual mode needs apv_begin_block / apv_finish_block");
+  if (nblocks == 0) return OK;
+  DevGuard dg(h->device);
   const Dims& D = h->D;
-  const size_t per = (size_t)D.V * D.H * D.L, pert = (size_t)D.H * D.L;
-  for (int b = 0; b < nblocks; ++b) {
-    APV_TRY(apv_process_block(h, in_A + (size_t)b * D.H, in_B + (size_t)b * D.H, out_A ? out_A + b * per : nullptr,
-                              out_B ? out_B + b * per : nullptr, out_A_t ? out_A_t + b * pert : nullptr,
-                              out_B_t ? out_B_t + b * pert : nullptr));
-    if (w_out) APV_TRY(apv_get(h, APV_T_W, w_out + (size_t)b * 2 * D.V * D.n, 2 * (size_t)D.V * D.n));
+  const size_t per = (size_t)D.V * D.H * D.L, pert = (size_t)D.H * D.L, perw = 2 * (size_t)D.V * D.n;
+  const size_t sd = ring_slot_doubles(D);
+  const int cap = sd * sizeof(double) > ((size_t)256 << 20) ? 2 : 3;
+  APV_TRY(ensure_ring(*h, cap));
+  double* d_sig = nullptr;       // [2][nblocks][H]
+  const size_t sig = (size_t)nblocks * D.H;
+  APV_CUDA_TRY(cudaMalloc((void**)&d_sig, 2 * sig * sizeof(double)));
+  int rc = OK;
+  auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == OK) rc = fail(ECUDA, "%s -> %s", what, cudaGetErrorString(e)); };
+  cu(cudaMemcpyAsync(d_sig, in_A, sig * sizeof(double), cudaMemcpyHostToDevice, h->st), "H2D in_A");
+  cu(cudaMemcpyAsync(d_sig + sig, in_B, sig * sizeof(double), cudaMemcpyHostToDevice, h->st), "H2D in_B");
+  const int ref = D.refA, lt = (D.J * ref + D.d) / D.J;
+  const int ltB = h->cfg.target_ref_per_zone ? (D.J * D.refB + D.d) / D.J : lt;
+  auto retire = [&](long b) {
+    const int rs = (int)(b % cap);
+    cu(cudaEventSynchronize(h->ev_d2h[rs]), "wait D2H");
+    if (rc != OK) return;
+    const double* src = h->ring_pin + (size_t)rs * sd;
+    const double* st_ = src + 2 * per + 2 * (size_t)D.H + perw;
+    int info[8];
+    memcpy(info, st_, sizeof(info));
+    const int s2 = status_from_info(*h, info, b);
+    if (s2 != OK) { rc = s2; return; }
+    if (out_A && D.runA) memcpy(out_A + (size_t)b * per, src, per * sizeof(double));
+    if (out_B && D.runB) memcpy(out_B + (size_t)b * per, src + per, per * sizeof(double));
+    const double* t = src + 2 * per;
+    for (int X = 0; X < 2; ++X) {
+      double* o = X == 0 ? out_A_t : out_B_t;
+      if (!o) continue;
+      o += (size_t)b * pert;
+      memset(o, 0, pert * sizeof(double));
+      const int col = X == 0 ? lt : ltB;
+      for (int i = 0; i < D.H; ++i) o[(size_t)i * D.L + col] = t[(size_t)X * D.H + i];
+    }
+    if (w_out) memcpy(w_out + (size_t)b * perw, src + 2 * per + 2 * (size_t)D.H, perw * sizeof(double));
+  };
+  for (long b = 0; b < nblocks && rc == OK; ++b) {
+    const int rs = (int)(b % cap);
+    double* slot = h->ring + (size_t)rs * sd;
+    if (b >= cap) cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
+    BlockSink sink{slot, slot + 2 * per, slot + 2 * per + 2 * (size_t)D.H,
+                   reinterpret_cast<int*>(slot + 2 * per + 2 * (size_t)D.H + perw)};
+    if (rc == OK) rc = enqueue_block(*h, b, d_sig + (size_t)b * D.H, d_sig + sig + (size_t)b * D.H, sink, false);
+    cu(cudaEventRecord(h->ev_rend[rs], h->st), "record");
+    cu(cudaStreamWaitEvent(h->st_copy, h->ev_rend[rs], 0), "wait render");
+    cu(cudaMemcpyAsync(h->ring_pin + (size_t)rs * sd, slot, sd * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy), "D2H");
+    cu(cudaEventRecord(h->ev_d2h[rs], h->st_copy), "record");
+    if (b >= 1 && rc == OK) retire(b - 1);
   }
-  return OK;
+  if (rc == OK) retire(nblocks - 1);
+  const int rc2 = leave_multiblock(*h);
+  cudaStreamSynchronize(h->st_front);
+  cudaStreamSynchronize(h->st_copy);
+  cudaStreamSynchronize(h->st);
+  cudaFree(d_sig);
+  return rc != OK ? rc : rc2;
 }
 
 int apv_process_block_device(apv_handle* h, const double* d_in_A, const double* d_in_B) {
   if (!h || !d_in_A || !d_in_B) return fail(EINVAL_, "null argument");
-  if (h->cfg.perceptual == 2) return fail(EINVAL_, "perceptual == 2 needs apv_begin_block / apv_finish_block");
+  if (h->cfg.perceptual >= 2) return fail(EINVAL_, "this perceptual mode needs apv_begin_block / apv_finish_block");
+  DevGuard dg(h->device);
   return run_block(*h, d_in_A, d_in_B, false, false);
 }
 
+// perceptual == 2: S1 + the windowed target frames for a host gain model; perceptual == 3: S1 + S2 with the on-device
+// masking model, after which the caller may overwrite weighting curves of other microphone groups (apv_copy_weights).
 int apv_begin_block(apv_handle* h, const double* in_A, const double* in_B) {
   if (!h || !in_A || !in_B) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   APV_TRY(copy_in(*h, in_A, in_B));
   h->launches = 0;
   APV_TRY(stage_fir(*h, h->d_in, h->d_in + h->D.H));
-  APV_TRY(stage_targets(*h, true));        // windowed target frames for the host gain model
+  APV_TRY(stage_targets(*h, h->cfg.perceptual != 3));   // 2: frames only; 3: the whole of S2
   h->began = true;
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   return OK;
@@ -387,6 +620,7 @@ int apv_begin_block(apv_handle* h, const double* in_A, const double* in_B) {
 
 int apv_finish_block(apv_handle* h, double* out_A, double* out_B, double* out_A_t, double* out_B_t) {
   if (!h || !h->began) return fail(EINVAL_, "apv_finish_block without apv_begin_block");
+  DevGuard dg(h->device);
   h->began = false;
   const int saved = h->launches;
   APV_TRY(run_block(*h, nullptr, nullptr, true, false));
@@ -395,17 +629,47 @@ int apv_finish_block(apv_handle* h, double* out_A, double* out_B, double* out_A_
   return check_info(*h);
 }
 
+int apv_copy_weights(apv_handle* dst, int dst_zone, int dst_mic0, apv_handle* src, int src_zone, int src_mic0, int n_mics) {
+  if (!dst || !src || n_mics < 0) return fail(EINVAL_, "bad argument");
+  if (dst->D.F != src->D.F) return fail(EINVAL_, "apv_copy_weights: block sizes differ");
+  if (dst_zone < 0 || dst_zone > 1 || src_zone < 0 || src_zone > 1 || dst_mic0 < 0 || src_mic0 < 0 ||
+      dst_mic0 + n_mics > dst->D.M || src_mic0 + n_mics > src->D.M)
+    return fail(EINVAL_, "apv_copy_weights: microphone range out of bounds");
+  if (dst->device != src->device) return fail(EINVAL_, "apv_copy_weights: handles on different devices");
+  DevGuard dg(dst->device);
+  const size_t F = dst->D.F;
+  APV_CUDA_TRY(cudaStreamSynchronize(src->st));
+  APV_CUDA_TRY(cudaMemcpyAsync(dst->Wg + ((size_t)dst_zone * dst->D.M + dst_mic0) * F,
+                               src->Wg + ((size_t)src_zone * src->D.M + src_mic0) * F, (size_t)n_mics * F * sizeof(double),
+                               cudaMemcpyDeviceToDevice, dst->st));
+  return OK;
+}
+
 int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B) {
   if (!h || !in_A || !in_B) return fail(EINVAL_, "null argument");
-  if (h->cfg.perceptual == 2) return fail(EINVAL_, "perceptual == 2 needs apv_begin_block / apv_finish_block");
+  if (h->cfg.perceptual >= 2) return fail(EINVAL_, "this perceptual mode needs apv_begin_block / apv_finish_block");
+  DevGuard dg(h->device);
   APV_TRY(copy_in(*h, in_A, in_B));
   APV_TRY(run_block(*h, h->d_in, h->d_in + h->D.H, false, true));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   return OK;
 }
 
+int apv_set_pipeline(apv_handle* h, int on) {
+  if (!h) return fail(EINVAL_, "null argument");
+  h->pipeline = on != 0;
+  return OK;
+}
+
+int apv_set_reg_mode(apv_handle* h, int relative) {
+  if (!h) return fail(EINVAL_, "null argument");
+  h->cfg.reg_relative = relative != 0;
+  return OK;
+}
+
 int apv_get(apv_handle* h, int id, double* dst, size_t count) {
   if (!h || !dst) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   TensorInfo ti = tensor_info(*h, id);
   if (!ti.ptr || count != ti.count) return fail(EINVAL_, "apv_get: bad tensor id %d or count %zu (want %zu)", id, count, ti.count);
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -421,6 +685,7 @@ int apv_get(apv_handle* h, int id, double* dst, size_t count) {
 
 int apv_set(apv_handle* h, int id, const double* src, size_t count) {
   if (!h || !src) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   TensorInfo ti = tensor_info(*h, id);
   if (!ti.ptr || count != ti.count) return fail(EINVAL_, "apv_set: bad tensor id %d or count %zu (want %zu)", id, count, ti.count);
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -442,6 +707,7 @@ int apv_set_mu(apv_handle* h, double mu) {
 
 int apv_set_gain_table(apv_handle* h, int n_channels, const double* G2, double Cs, double Ca, double Leff) {
   if (!h || !G2 || n_channels < 1) return fail(EINVAL_, "bad argument");
+  DevGuard dg(h->device);
   if (h->G2) cudaFree(h->G2);
   h->G2 = nullptr;
   const size_t cnt = (size_t)n_channels * h->D.F;
@@ -453,6 +719,7 @@ int apv_set_gain_table(apv_handle* h, int n_channels, const double* G2, double C
 
 int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out) {
   if (!h || !mu || !w_out || n_mu < 1) return fail(EINVAL_, "bad argument");
+  DevGuard dg(h->device);
   const Dims& D = h->D;
   const size_t cnt = 2 * (size_t)D.V * D.n;
   double* tmp = nullptr;
@@ -471,6 +738,7 @@ int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out) {
 
 int apv_eval_zone(apv_handle* h, int zone, int n_samples, const double* feeds, const double* signal, double* out3) {
   if (!h || !feeds || !signal || !out3) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   return eval_zone(*h, zone, n_samples, feeds, signal, out3);
 }
 
@@ -484,24 +752,32 @@ int apv_device_ptr(apv_handle* h, int id, void** ptr) {
 
 int apv_synchronize(apv_handle* h) {
   if (!h) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st_front));
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st_copy));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   return OK;
 }
 
 int apv_stage_times(apv_handle* h, float* ms7) {
   if (!h || !ms7) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st_front));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  // front half: ev[0] .. ev[3]; back half: ev[7], ev[4] .. ev[6] (they overlap other blocks in a multi-block call)
+  const int from[6] = {0, 1, 2, 7, 4, 5}, to[6] = {1, 2, 3, 4, 5, 6};
+  ms7[6] = 0.f;
   for (int i = 0; i < 6; ++i) {
     ms7[i] = 0.f;
-    cudaEventElapsedTime(&ms7[i], h->ev[i], h->ev[i + 1]);
+    cudaEventElapsedTime(&ms7[i], h->ev[from[i]], h->ev[to[i]]);
+    ms7[6] += ms7[i];
   }
-  ms7[6] = 0.f;
-  cudaEventElapsedTime(&ms7[6], h->ev[0], h->ev[6]);
   return OK;
 }
 
 int apv_jdiag_phase_times(apv_handle* h, float* ms6) {
   if (!h || !ms6) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   for (int i = 0; i < 6; ++i) ms6[i] = 0.f;
   if (h->nz == 0) return OK;
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -511,7 +787,9 @@ int apv_jdiag_phase_times(apv_handle* h, float* ms6) {
 
 int apv_kernel_times(apv_handle* h, float* ms4) {
   if (!h || !ms4) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   for (int i = 0; i < 4; ++i) ms4[i] = 0.f;
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st_front));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   if (h->nz > 0) {
     cudaEventElapsedTime(&ms4[1], h->ev_syrk[0], h->ev_syrk[1]);
@@ -535,6 +813,7 @@ int apv_kernel_times(apv_handle* h, float* ms4) {
 
 int apv_timer_start(apv_handle* h) {
   if (!h) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   APV_CUDA_TRY(cudaEventRecord(h->ev_timer[0], h->st));
   return OK;
@@ -542,6 +821,7 @@ int apv_timer_start(apv_handle* h) {
 
 int apv_timer_stop(apv_handle* h, float* ms) {
   if (!h || !ms) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
   APV_CUDA_TRY(cudaEventRecord(h->ev_timer[1], h->st));
   APV_CUDA_TRY(cudaEventSynchronize(h->ev_timer[1]));
   APV_CUDA_TRY(cudaEventElapsedTime(ms, h->ev_timer[0], h->ev_timer[1]));

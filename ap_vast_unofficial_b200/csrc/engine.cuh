@@ -63,15 +63,18 @@ int twostage_nsplit_max();
 int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches);   // then by the stage-1 block reflectors -> Zt
+// regv != nullptr: per-zone diagonal loading read from device memory instead of `reg`.
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
-              cudaStream_t st, int* launches);
+              cudaStream_t st, int* launches, const double* regv = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 struct Handle {
   apv_config cfg;
   Dims D;
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t st = nullptr;       // main stream (highest priority): S5-S7, and S1-S4 too in the per-block call
+  cudaStream_t st_front = nullptr; // low-priority stream: S1-S4 of block t+1 while S5-S7 of block t run on `st`
+  cudaStream_t st_copy = nullptr;  // D2H of the rendered outputs of the multi-block call
+  cudaEvent_t ev[8] = {};          // [0] front start [1] S1 [2] S3 [3] S4 | [7] back start [4] S5 [5] S6 [6] S7
   cudaEvent_t ev_syrk[2] = {};   // around the statistics SYRK kernel
   cudaEvent_t ev_timer[2] = {};  // apv_timer_start / apv_timer_stop
   int device = 0;
@@ -103,9 +106,18 @@ struct Handle {
   double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)
   double* G = nullptr;       // [2][V][L][Nb]
   double* Gt = nullptr;      // [2][Nb]
-  // results
+  // results.  R, rvec and xw exist in two slots so that the statistics of block t+1 can be formed while block t is
+  // still being diagonalised and rendered (apv_process_blocks / apv_range_run); R, rvec, xw point at the slot of the
+  // block whose S5-S7 ran last.
+  double* Rslot[2] = {nullptr, nullptr};     // [4][n][ldn]
+  double* rvslot[2] = {nullptr, nullptr};    // [2][n]
+  double* xwslot[2] = {nullptr, nullptr};    // [2][Nb]  window * input block (what S7 filters, apvast.py:430-431)
+  cudaEvent_t ev_ready[2] = {};              // front of the slot finished (statistics ready)
+  cudaEvent_t ev_free[2] = {};               // back of the slot finished (slot may be overwritten)
   double* R = nullptr;       // [4][n][ldn]
   double* rvec = nullptr;    // [2][n]
+  double* xw = nullptr;      // [2][Nb]
+  double* regv = nullptr;    // [2] per-zone diagonal loading when EXPERIMENTAL_REGULARIZATION is off (apvast.py:25-27)
   double* lam = nullptr;     // [2][V]
   double* U = nullptr;       // [2][V][n]
   double* W = nullptr;       // [2][V][n]
@@ -115,6 +127,33 @@ struct Handle {
   double* d_out_t = nullptr; // [2][H]
   double* h_pin = nullptr;   // pinned host staging
   size_t h_pin_count = 0;
+  double* home_W = nullptr;  // the buffers W / d_out / d_out_t point at outside a multi-block call
+  double* home_out = nullptr;
+  double* home_out_t = nullptr;
+  // multi-block call: ring of rendered blocks in HBM + pinned host ring for the asynchronous D2H
+  double* ring = nullptr;    // [ring_cap] x (out 2 V H L | out_t 2 H | W 2 V n)
+  int ring_cap = 0;
+  double* ring_pin = nullptr;
+  int ring_pin_cap = 0;
+  int* ring_info = nullptr;  // pinned [ring_pin_cap][8]
+  cudaEvent_t ev_rend[4] = {};   // block rendered into its ring slot
+  cudaEvent_t ev_d2h[4] = {};    // ring slot copied to the pinned ring
+  int pipeline = 1;          // 0: S1-S7 of consecutive blocks strictly in order on one stream
+  // block-range sharding (comm.cu)
+  double* rg_out = nullptr;  // [rg_cap][2][V][H][L] rendered outputs of the owned blocks
+  double* rg_w = nullptr;    // [rg_cap][2][V][n]    filters of the owned blocks
+  int* rg_info = nullptr;    // [rg_cap][8] jdiag status of the owned blocks
+  int rg_cap = 0, rg_owned = 0;
+  double* rg_sig = nullptr;  // [2][halo + owned][H] hops of a range copied from the host
+  size_t rg_sig_cap = 0;
+  int* gat_info = nullptr;   // root: [total blocks][8]
+  double* rg_tail_send = nullptr;  // [2][V][L][Nb-H]
+  double* rg_tail_recv = nullptr;
+  double* gat_out = nullptr; // root: [total blocks][2][V][H][L]
+  double* gat_w = nullptr;   // root: [total blocks][2][V][n]
+  int gat_cap = 0;
+  void* comm = nullptr;      // ncclComm_t
+  int comm_rank = 0, comm_size = 1;
   JdiagWs jd;
   int nz = 0;
   int zones[2] = {0, 1};
@@ -124,7 +163,7 @@ struct Handle {
 };
 
 // stage launchers (each returns status; `launches` is incremented per kernel launch)
-int stage_fir(Handle& h, const double* d_inA, const double* d_inB);           // S1 (fir_wola.cu)
+int stage_fir(Handle& h, const double* d_inA, const double* d_inB);           // S1 (fir_wola.cu); also fills h.xw
 int stage_targets(Handle& h, bool compute_gain);                              // S2 + S2b
 int stage_weighted(Handle& h);                                                // S3
 int stage_stats(Handle& h);                                                   // S4 (stats.cu)
@@ -132,7 +171,34 @@ int stage_loading(Handle& h);                                                 //
 int stage_sweep(Handle& h, double mu, double* W_out);                         // S6 (render.cu)
 int stage_render(Handle& h);                                                  // a2 + S7
 int eval_zone(Handle& h, int zone, int T, const double* feeds, const double* signal, double* out3);  // metrics.cu
+int stage_spectral_norms(Handle& h);                                          // |R_D|_2 per zone -> regv (stats.cu)
 int fft_plan(int n, int* rad, int* nrad);
+// engine.cu internals used by comm.cu
+int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only);
+int run_back(Handle& h);
+int fail(int code, const char* fmt, ...);
+struct DevGuard {   // entry points run on the handle's device whatever the caller's current device is
+  int prev = -1, dev = -1;
+  explicit DevGuard(int d) : dev(d) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev != dev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+struct BlockSink {   // device destinations of one block's results (nullptr = the handle's own buffers)
+  double* out;     // [2][V][H][L]
+  double* out_t;   // [2][H]
+  double* W;       // [2][V][n]
+  int* info;       // [8] status of the joint diagonalisation
+};
+bool pipelined(const Handle& h);
+int enqueue_block(Handle& h, long b, const double* d_inA, const double* d_inB, const BlockSink& sink, bool state_only);
+int leave_multiblock(Handle& h);
+int status_from_info(const Handle& h, const int* info, long block);
+int range_alloc(Handle& h, int max_owned, int total_on_root);
+void range_free(Handle& h);
 int fft_util(int n, int inverse, const double* in_ri, double* out_ri);        // test hook
 
 }  // namespace apv

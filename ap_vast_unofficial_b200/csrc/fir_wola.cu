@@ -60,12 +60,19 @@ struct FftPlan {
 
 // ------------------------------------------------------------------------------------------
 // xin[X][LX] <- [xin[X][H:], new]   (also serves update_input_blocks, apvast.py:424-426)
+// and xw[X][s] = win[s] * x_X[s], the windowed input block S7 filters (apvast.py:430-431): a snapshot per block, so
+// that rendering block t does not depend on xin once S1 of block t+1 has shifted it.
 __global__ void input_shift_kernel(double* __restrict__ xin, const double* __restrict__ inA,
-                                   const double* __restrict__ inB, int LX, int H) {
+                                   const double* __restrict__ inB, const double* __restrict__ win,
+                                   double* __restrict__ xw, int LX, int H, int Nb) {
   double* x = xin + (size_t)blockIdx.x * LX;
   const double* in = blockIdx.x == 0 ? inA : inB;
   for (int i = threadIdx.x; i < H; i += blockDim.x)
     for (int j = i; j < LX; j += H) x[j] = (j + H < LX) ? x[j + H] : in[j + H - LX];
+  __syncthreads();
+  const double* xb = x + (LX - Nb);
+  double* o = xw + (size_t)blockIdx.x * Nb;
+  for (int s = threadIdx.x; s < Nb; s += blockDim.x) o[s] = win[s] * xb[s];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,7 +294,7 @@ int fft_plan(int n, int* rad, int* nrad) {
 
 int stage_fir(Handle& h, const double* d_inA, const double* d_inB) {
   const Dims& D = h.D;
-  input_shift_kernel<<<2, 256, 0, h.st>>>(h.xin, d_inA, d_inB, D.LX, D.H);
+  input_shift_kernel<<<2, 256, 0, h.st>>>(h.xin, d_inA, d_inB, h.win, h.xw, D.LX, D.H, D.Nb);
   size_t sm = (size_t)(2 * D.K - 1 + 2 * D.H) * sizeof(double);
   APV_TRY(ensure_smem(fir_kernel, sm));
   fir_kernel<<<dim3(D.L, D.M, 6), 256, sm, h.st>>>(h.xin, h.rirT, h.rirTT, h.Q, h.QT, D);

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256, 2) gemm_async_kernel(GemmArgs g) {
 template <int TB, int BN>
 int launch_async(const GemmArgs& g, cudaStream_t st) {
   using Cfg = AsyncCfg<TB, BN>;
-  static thread_local bool configured = false;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (!configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(gemm_async_kernel<TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
@@ -309,7 +309,7 @@ int launch_async(const GemmArgs& g, cudaStream_t st) {
 
 template <int TA, int TB, int BN>
 int launch_bn(const GemmArgs& g, cudaStream_t st) {
-  static thread_local bool configured = false;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (!configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       smem_bytes(BN)));

@@ -34,8 +34,9 @@ struct Ptr2 {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void prep_kernel(Ptr2 bright, Ptr2 dark, int ld_in, double* __restrict__ Cm, double* __restrict__ Lm,
-                            int n, int ldn, double reg) {
+                            int n, int ldn, double reg, const double* __restrict__ regv) {
   const int z = blockIdx.z;
+  if (regv) reg = regv[z];      // per-zone loading computed on the device (norm-relative, apvast.py:25-27)
   const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const size_t o = ((size_t)z * n + i) * ldn + j;
@@ -1177,7 +1178,7 @@ static int trsm_lower(JdiagWs& ws, double* X, double* Y, int m, int ldx, long lo
 }
 
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
-              cudaStream_t st, int* launches) {
+              cudaStream_t st, int* launches, const double* regv) {
   const int n = ws.n, ldn = ws.ldn, nz = ws.nz, V = ws.V;
   const long long mstride = (long long)n * ldn;
   int nl = 0;
@@ -1185,7 +1186,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   APV_CUDA_TRY(cudaMemsetAsync(ws.info, 0, (size_t)nz * 4 * sizeof(int), st));
   Ptr2 pb, pd;
   for (int z = 0; z < 2; ++z) { pb.p[z] = bright[z < nz ? z : 0]; pd.p[z] = dark[z < nz ? z : 0]; }
-  prep_kernel<<<dim3(ceil_div(n, 256), n, nz), 256, 0, st>>>(pb, pd, ld_in, ws.Cm, ws.Lm, n, ldn, reg);
+  prep_kernel<<<dim3(ceil_div(n, 256), n, nz), 256, 0, st>>>(pb, pd, ld_in, ws.Cm, ws.Lm, n, ldn, reg, regv);
   ++nl;
 
   // ---- blocked Cholesky of Lm (lower)

@@ -85,7 +85,7 @@ int eval_zone(Handle& h, int zone, int T, const double* feeds, const double* sig
   APV_CUDA_TRY(cudaMemcpyAsync(d_f, feeds, (size_t)T * D.L * sizeof(double), cudaMemcpyHostToDevice, h.st));
   APV_CUDA_TRY(cudaMemcpyAsync(d_s, signal, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, h.st));
   const size_t sm = (size_t)(2 * D.K - 1 + MT) * sizeof(double);
-  static thread_local size_t configured = 0;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (sm > 48 * 1024 && sm > configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(pressure_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     configured = sm;

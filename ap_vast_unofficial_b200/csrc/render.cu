@@ -7,6 +7,8 @@
 //                   Here it is evaluated directly in the time domain (J taps x Nb samples per
 //                   (rank, loudspeaker)), fused with the window, the in-place overlap-add shift and
 //                   the (V, H, L) output transpose.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace apv {
@@ -45,59 +47,119 @@ __global__ void __launch_bounds__(256) sweep_prefix_kernel(const double* __restr
   }
 }
 
-// S7 for the controlled streams.  grid (L, V, nz).  smem: xe[Nb + J - 1] + tr[J].
-__global__ void __launch_bounds__(256) render_kernel(const double* __restrict__ xin, const double* __restrict__ W,
+// S7 for the controlled streams.  grid (H / RT, V, nz), 256 threads.  A CTA renders a tile of RT hop positions (and
+// the Nb/H - 1 overlap positions behind each of them) of ALL loudspeakers of one (zone, rank): lane = hop position, so
+// the overlap buffer is read and written with unit stride and the tap loop reads the filter by broadcast; every warp
+// works on two loudspeakers at a time (one shared-memory load per FMA instead of two).  The (RT, L) output tile is
+// staged in shared memory and leaves as one contiguous run of double2 (the (V, H, L) layout of the reference's output
+// lists).  Only the first min(J, Nb) taps act: rfft(w, Nb) crops the filter (apvast.py:417-420).
+constexpr int RT = 64;       // hop positions per CTA
+
+struct RenderPlan {
+  int LC;       // loudspeakers per shared-memory pass
+  int Je;       // taps that act = min(J, Nb)
+  int ncls;     // residue classes = ceil(Nb / H)
+  size_t smem;
+};
+
+__global__ void __launch_bounds__(256) render_kernel(const double* __restrict__ xw, const double* __restrict__ W,
                                                      const double* __restrict__ win, double* __restrict__ G,
-                                                     double* __restrict__ out, Dims D, int zone0, int zone1) {
-  extern __shared__ double sm[];
-  const int Nb = D.Nb, J = D.J, H = D.H;
-  double* xe = sm;               // xe[t] = xw[(t - (J-1)) mod Nb]
-  double* tr = sm + Nb + J - 1;  // tr[j'] = w[J-1-j']
-  const int l = blockIdx.x, v = blockIdx.y, zone = blockIdx.z == 0 ? zone0 : zone1;
-  const double* x = xin + (size_t)zone * D.LX + (D.LX - Nb);
-  const double* w = W + ((size_t)zone * D.V + v) * D.n + (size_t)l * J;
-  for (int t = threadIdx.x; t < Nb + J - 1; t += blockDim.x) {
-    int s = t - (J - 1);
-    s %= Nb;
+                                                     double* __restrict__ out, Dims D, int zone0, int zone1, int LC,
+                                                     int Je, int ncls) {
+  extern __shared__ __align__(16) double sm[];
+  const int Nb = D.Nb, J = D.J, H = D.H, L = D.L;
+  const int XS = RT + Je - 1 + 1;                 // padded length of one class window
+  double* tr = sm;                                // [LC][Je]   tr[l][k'] = w[l][Je-1-k']
+  double* xe = tr + (size_t)LC * Je;              // [ncls][XS] xe[c][t] = xw[(h0 + c H + t - (Je-1)) mod Nb]
+  double* ot = xe + (size_t)ncls * XS;            // [RT][L]    output tile
+  const int h0 = blockIdx.x * RT, v = blockIdx.y, zone = blockIdx.z == 0 ? zone0 : zone1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* x = xw + (size_t)zone * Nb;
+  for (int e = tid; e < ncls * XS; e += 256) {
+    const int c = e / XS, t = e - c * XS;
+    int s = (h0 + c * H + t - (Je - 1)) % Nb;
     if (s < 0) s += Nb;
-    xe[t] = win[s] * x[s];
+    xe[e] = (t < RT + Je - 1) ? x[s] : 0.0;
   }
-  for (int j = threadIdx.x; j < J; j += blockDim.x) tr[j] = w[J - 1 - j];
-  __syncthreads();
-  double* g = G + (((size_t)zone * D.V + v) * D.L + l) * Nb;
-  double* o = out + ((size_t)zone * D.V + v) * H * D.L + l;
-  // thread i < H owns the residue class {i, i+H, ...} of the overlap buffer
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    for (int j = i; j < Nb; j += H) {
-      double a0 = 0.0, a1 = 0.0;
-      const double* xp = xe + j;
-      int k = 0;
-      for (; k + 1 < J; k += 2) {
-        a0 = fma(tr[k], xp[k], a0);
-        a1 = fma(tr[k + 1], xp[k + 1], a1);
-      }
-      if (k < J) a0 = fma(tr[k], xp[k], a0);
-      const double val = ((j + H < Nb) ? g[j + H] : 0.0) + win[j] * (a0 + a1);
-      g[j] = val;
-      if (j == i) o[(size_t)i * D.L] = val;
+  const double* wz = W + ((size_t)zone * D.V + v) * D.n;
+  double* gz = G + ((size_t)zone * D.V + v) * L * Nb;
+  for (int l0 = 0; l0 < L; l0 += LC) {
+    const int lc = min(LC, L - l0);
+    __syncthreads();
+    for (int e = tid; e < lc * Je; e += 256) {
+      const int l = e / Je, k = e - l * Je;
+      tr[e] = wz[(size_t)(l0 + l) * J + (Je - 1 - k)];
     }
+    __syncthreads();
+    for (int lp = 2 * warp; lp < lc; lp += 16) {          // loudspeaker pair (lp, lp + 1)
+      const bool two = lp + 1 < lc;
+      const double* t0 = tr + (size_t)lp * Je;
+      const double* t1 = tr + (size_t)(two ? lp + 1 : lp) * Je;
+      for (int c = 0; c < ncls; ++c) {
+        const double* xc = xe + (size_t)c * XS + lane;
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;     // [loudspeaker][hop position lane / lane + 32]
+        double b00 = 0.0, b01 = 0.0, b10 = 0.0, b11 = 0.0;     // odd taps
+        int k = 0;
+        for (; k + 1 < Je; k += 2) {
+          const double w0 = t0[k], w0b = t0[k + 1], w1 = t1[k], w1b = t1[k + 1];
+          const double x0 = xc[k], x0b = xc[k + 1], x1 = xc[k + 32], x1b = xc[k + 33];
+          a00 = fma(w0, x0, a00); a01 = fma(w0, x1, a01);
+          a10 = fma(w1, x0, a10); a11 = fma(w1, x1, a11);
+          b00 = fma(w0b, x0b, b00); b01 = fma(w0b, x1b, b01);
+          b10 = fma(w1b, x0b, b10); b11 = fma(w1b, x1b, b11);
+        }
+        if (k < Je) {
+          const double w0 = t0[k], w1 = t1[k], x0 = xc[k], x1 = xc[k + 32];
+          a00 = fma(w0, x0, a00); a01 = fma(w0, x1, a01);
+          a10 = fma(w1, x0, a10); a11 = fma(w1, x1, a11);
+        }
+        const double y[2][2] = {{a00 + b00, a01 + b01}, {a10 + b10, a11 + b11}};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          double* g = gz + (size_t)(l0 + lp + q) * Nb;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int hl = lane + 32 * u, h = h0 + hl;
+            const int j = h + c * H;
+            if (h < H && j < Nb) {
+              // in-place overlap-add shift: class c of position h is read (g[j + H]) before class c + 1 overwrites it
+              const double val = ((j + H < Nb) ? g[j + H] : 0.0) + win[j] * y[q][u];
+              g[j] = val;
+              if (c == 0) ot[(size_t)hl * L + l0 + lp + q] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int rows = min(RT, H - h0);
+  double* o = out + ((size_t)zone * D.V + v) * H * L + (size_t)h0 * L;
+  const int cnt = rows * L;
+  if ((cnt & 1) == 0 && ((reinterpret_cast<size_t>(o) & 15) == 0)) {
+    double2* o2 = reinterpret_cast<double2*>(o);
+    const double2* s2 = reinterpret_cast<const double2*>(ot);
+    for (int e = tid; e < cnt / 2; e += 256) o2[e] = s2[e];
+  } else {
+    for (int e = tid; e < cnt; e += 256) o[e] = ot[e];
   }
 }
 
 // Target streams: filter_target is a unit impulse (apvast.py:389-390), so the frame is a circular delay of the
 // windowed input on one loudspeaker.  grid (2 signals).
-__global__ void __launch_bounds__(256) render_target_kernel(const double* __restrict__ xin, const double* __restrict__ win,
+__global__ void __launch_bounds__(256) render_target_kernel(const double* __restrict__ xw, const double* __restrict__ win,
                                                             double* __restrict__ Gt, double* __restrict__ out_t, Dims D,
                                                             int tap) {
   const int Nb = D.Nb, H = D.H;
   const int X = blockIdx.x;
-  const double* x = xin + (size_t)X * D.LX + (D.LX - Nb);
+  const double* x = xw + (size_t)X * Nb;
   double* g = Gt + (size_t)X * Nb;
   for (int i = threadIdx.x; i < H; i += blockDim.x)
     for (int j = i; j < Nb; j += H) {
       int s = (j - tap) % Nb;
       if (s < 0) s += Nb;
-      const double val = ((j + H < Nb) ? g[j + H] : 0.0) + win[j] * (win[s] * x[s]);
+      const double val = ((j + H < Nb) ? g[j + H] : 0.0) + win[j] * x[s];
       g[j] = val;
       if (j == i) out_t[(size_t)X * H + i] = val;
     }
@@ -120,17 +182,29 @@ int stage_sweep(Handle& h, double mu, double* W_out) {
 int stage_render(Handle& h) {
   const Dims& D = h.D;
   if (h.nz > 0) {
-    const size_t sm = (size_t)(D.Nb + 2 * D.J - 1) * sizeof(double);
-    static thread_local size_t configured = 0;
-    if (sm > 48 * 1024 && sm > configured) {
-      APV_CUDA_TRY(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      configured = sm;
+    RenderPlan rp;
+    rp.Je = std::min(D.J, D.Nb);
+    rp.ncls = ceil_div(D.Nb, D.H);
+    const size_t fixed = ((size_t)rp.ncls * (RT + rp.Je) + (size_t)RT * D.L) * sizeof(double);
+    rp.LC = D.L;
+    while (rp.LC > 2 && fixed + (size_t)rp.LC * rp.Je * sizeof(double) > 160 * 1024) rp.LC = (rp.LC + 1) / 2;
+    rp.LC = std::max(2, (rp.LC + 1) & ~1);       // warps work on loudspeaker pairs
+    rp.smem = fixed + (size_t)rp.LC * rp.Je * sizeof(double);
+    if (rp.smem > 220 * 1024) {
+      snprintf(g_err, sizeof(g_err), "render: block/filter sizes need %zu B of shared memory", rp.smem);
+      return EINVAL_;
     }
-    render_kernel<<<dim3(D.L, D.V, h.nz), 256, sm, h.st>>>(h.xin, h.W, h.win, h.G, h.d_out, D, h.zones[0], h.zones[1]);
+    static PerDevice pd_configured; size_t& configured = pd_configured.cur();
+    if (rp.smem > 48 * 1024 && rp.smem > configured) {
+      APV_CUDA_TRY(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem));
+      configured = rp.smem;
+    }
+    render_kernel<<<dim3(ceil_div(D.H, RT), D.V, h.nz), 256, rp.smem, h.st>>>(h.xw, h.W, h.win, h.G, h.d_out, D, h.zones[0],
+                                                                            h.zones[1], rp.LC, rp.Je, rp.ncls);
     h.launches += 1;
   }
   const int tgt = D.J * D.refA + D.d;      // reference uses reference_index_A for both targets (:418,422)
-  render_target_kernel<<<2, 256, 0, h.st>>>(h.xin, h.win, h.Gt, h.d_out_t, D, tgt % D.J);
+  render_target_kernel<<<2, 256, 0, h.st>>>(h.xw, h.win, h.Gt, h.d_out_t, D, tgt % D.J);
   h.launches += 1;
   APV_CUDA_TRY(cudaGetLastError());
   return OK;

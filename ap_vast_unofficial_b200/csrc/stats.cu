@@ -408,7 +408,7 @@ __global__ void diag_load_kernel(double* __restrict__ R, const double* __restric
 
 // MATLAB diagonalLoading (apVast.m:552-569): spectral norms by power iteration (run to convergence of the estimate),
 // then bright += 1e-8 |R_B|_2 I and dark += 5e-3 |R_D|_2 I on the stored statistics.
-int stage_loading(Handle& h) {
+static int power_norms(Handle& h) {
   const Dims& D = h.D;
   const int n = D.n;
   double* x = h.pvec;
@@ -428,7 +428,30 @@ int stage_loading(Handle& h) {
       if (fabs(hn[p] - hn[4 + p]) > 1e-15 * fabs(hn[p])) done = false;
     if (done) break;
   }
-  diag_load_kernel<<<dim3(ceil_div(n, 256), 4), 256, 0, h.st>>>(h.R, h.norms, n, D.ldn, h.cfg.bright_load, h.cfg.dark_load);
+  return OK;
+}
+
+int stage_loading(Handle& h) {
+  const Dims& D = h.D;
+  APV_TRY(power_norms(h));
+  diag_load_kernel<<<dim3(ceil_div(D.n, 256), 4), 256, 0, h.st>>>(h.R, h.norms, D.n, D.ldn, h.cfg.bright_load, h.cfg.dark_load);
+  h.launches += 1;
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
+// EXPERIMENTAL_REGULARIZATION = False (apvast.py:25-27): the dark matrix of every zone problem is loaded with
+// 1e-8 |R_D|_2 instead of the absolute 1e-7.  regv[zi] for the zone order of the joint diagonalisation.
+__global__ void regv_kernel(const double* __restrict__ norms, double* __restrict__ regv, int zone0, int zone1, double coef) {
+  if (threadIdx.x < 2) {
+    const int zone = threadIdx.x == 0 ? zone0 : zone1;
+    regv[threadIdx.x] = coef * norms[zone == 0 ? 1 : 2];      // dark paths: A->B (1) for zone A, B->A (2) for zone B
+  }
+}
+
+int stage_spectral_norms(Handle& h) {
+  APV_TRY(power_norms(h));
+  regv_kernel<<<1, 32, 0, h.st>>>(h.norms, h.regv, h.zones[0], h.zones[1], 1e-8);
   h.launches += 1;
   APV_CUDA_TRY(cudaGetLastError());
   return OK;
@@ -446,7 +469,7 @@ int stage_stats(Handle& h) {
     snprintf(g_err, sizeof(g_err), "stats_syrk: filter_length %d too small for the tile staging (%zu B smem)", D.J, sm);
     return EINVAL_;
   }
-  static thread_local size_t configured = 0;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (sm > configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(syrk_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     configured = sm;
@@ -456,7 +479,7 @@ int stage_stats(Handle& h) {
   if (h.cfg.stats_mode == 2) {
     if (D.J > 1024) return EINVAL_;
     const size_t ssm = (size_t)(2 * D.P + D.J) * sizeof(double);
-    static thread_local size_t conf2 = 0;
+    static PerDevice pd_conf2; size_t& conf2 = pd_conf2.cur();
     if (ssm > 48 * 1024 && ssm > conf2) {
       APV_CUDA_TRY(cudaFuncSetAttribute(stats_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
       conf2 = ssm;

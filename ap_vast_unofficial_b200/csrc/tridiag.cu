@@ -387,7 +387,7 @@ int tridiag_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   APV_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int G = std::max(1, std::min(std::min(sms / nz, GMAX), ceil_div(n, 16)));
   const size_t smem = (size_t)(ldn + TD_EXTRA) * sizeof(double);
-  static thread_local size_t configured = 0;
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
   if (smem > 48 * 1024 && smem > configured) {
     APV_CUDA_TRY(cudaFuncSetAttribute(td_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -37,13 +37,16 @@ def _programme(seed, n, fs=48000.0):
     return x / np.sqrt(np.mean(x * x))
 
 
-def make_workload(name: str, n_blocks: int = None):
+def make_workload(name: str, n_blocks: int = None, variant: int = 0):
+    """`variant` > 0 selects another deterministic draw of the RIRs and the programme signals (parity fixtures)."""
     c = CONFIGS[name]
+    vs = 100 * int(variant)
     H = c["Nb"] // 2
     total = int(c["seconds"] * 48000) // H if n_blocks is None else n_blocks
     n = total * H
     cfg = dict(block_size=c["Nb"], filter_length=c["J"], modeling_delay=c["d"], reference_index_A=0,
                reference_index_B=0, number_of_eigenvectors=c["V"], mu=1.0, statistics_buffer_length=c["N"])
-    return dict(name=name, cfg=cfg, rir_A=_rirs(10, c["K"], c["L"], c["M"]), rir_B=_rirs(11, c["K"], c["L"], c["M"]),
-                signal_A=_programme(1, n), signal_B=_programme(2, n), n_blocks=total, hop=H,
+    return dict(name=name, cfg=cfg, rir_A=_rirs(10 + vs, c["K"], c["L"], c["M"]),
+                rir_B=_rirs(11 + vs, c["K"], c["L"], c["M"]),
+                signal_A=_programme(1 + vs, n), signal_B=_programme(2 + vs, n), n_blocks=total, hop=H,
                 shapes=dict(c, H=H, n=c["L"] * c["J"]))

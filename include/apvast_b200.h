@@ -30,7 +30,8 @@ enum apv_status {
   APV_ENOTPD = 2,  /* R_D + reg*I not positive definite (reference: numpy LinAlgError, apvast.py:21-24) */
   APV_ECUDA = 3,   /* CUDA runtime error */
   APV_ENOMEM = 4,
-  APV_ENOCONV = 5  /* eigen-solver did not converge */
+  APV_ENOCONV = 5, /* eigen-solver did not converge */
+  APV_ENCCL = 6    /* NCCL error (block-range sharding) */
 };
 
 /* Constructor parameters: reference apvast.__init__ (apvast.py:40-56) + module flags (:6-7). */
@@ -47,7 +48,10 @@ typedef struct apv_config {
   int32_t ref_A, ref_B;      /* reference_index_A/B, 0-based      (:46-47)                          */
   int32_t run_A, run_B;      /* (:53-54)                                                            */
   int32_t perceptual;        /* 0: W == 1 (:326-327); 1: on-device masking model (apv_set_gain_table);
-                                2: weighting spectra supplied by the host per block (apv_set_weights) */
+                                2: weighting spectra supplied by the host per block (apv_begin_block, APV_T_WEIGHT);
+                                3: on-device model, split call: apv_begin_block runs S1 + S2, the caller may then
+                                   exchange weighting curves between handles (apv_copy_weights), apv_finish_block
+                                   runs S3..S7 */
   int32_t normalize_gains;   /* EXPERIMENTAL_NORMALIZE_GAINS (:6,322-324)                           */
   int32_t eig_mode;          /* 0 auto (2 for n <= 48, 3 for n >= 1024, else 1);
                                 1 one-stage Householder tridiagonalisation + bisection + inverse
@@ -74,7 +78,8 @@ typedef struct apv_config {
   /* more than two zones by composition (zones.py): the microphones m >= active_mics_A of zone A are silent padding
      (zero RIRs) and are skipped by the statistics; 0 = all n_mics are real */
   int32_t active_mics_A;
-  int32_t reserved0;
+  int32_t reg_relative;      /* EXPERIMENTAL_REGULARIZATION off (apvast.py:25-27): dark += 1e-8 |R_D|_2 I inside
+                                jdiag instead of the absolute `reg` (spectral norm by power iteration)        */
 } apv_config;
 
 typedef struct apv_handle apv_handle;
@@ -119,9 +124,12 @@ void apv_destroy(apv_handle* h);
 int apv_process_block(apv_handle* h, const double* in_A, const double* in_B, double* out_A, double* out_B,
                       double* out_A_t, double* out_B_t);
 
-/* Throughput path: nblocks consecutive hops in one call; identical results.  in_*: (nblocks, H);
- * out_A/out_B: (nblocks, V, H, L) or NULL; out_*_t: (nblocks, H, L) or NULL;
- * w_out: (nblocks, 2, V, n) or NULL (per-block filters). */
+/* Throughput path: nblocks consecutive hops in one call; results identical to nblocks per-block calls (the caller of
+ * the reference is a plain per-hop loop, make_python_test.m:44-54).  The hops are copied to the device once; S1-S4 of
+ * block t+1 (which depend on the streaming state only, apvast.py:329-364) run on a second, low-priority stream while
+ * S5-S7 of block t occupy the main stream; rendered blocks leave through a ring in HBM, a copy stream and a pinned host
+ * ring, one block behind.  in_*: (nblocks, H); out_A/out_B: (nblocks, V, H, L) or NULL; out_*_t: (nblocks, H, L) or
+ * NULL; w_out: (nblocks, 2, V, n) or NULL (per-block filters). */
 int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const double* in_B, double* out_A,
                        double* out_B, double* out_A_t, double* out_B_t, double* w_out);
 
@@ -136,6 +144,46 @@ int apv_finish_block(apv_handle* h, double* out_A, double* out_B, double* out_A_
 
 /* Warm-up only: S1-S3 (state update) without statistics / filters / rendering (multi-GPU halo). */
 int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B);
+
+/* 0: consecutive blocks of a multi-block call strictly in order on one stream; 1 (default, also env APV_PIPELINE):
+ * S1-S4 of block t+1 overlap S5-S7 of block t.  Results are bit-identical either way. */
+int apv_set_pipeline(apv_handle* h, int on);
+/* EXPERIMENTAL_REGULARIZATION (apvast.py:7,22-27), read by the reference at call time: 0 = absolute reg (default),
+ * 1 = 1e-8 |R_D|_2 (spectral norm by power iteration on the device). */
+int apv_set_reg_mode(apv_handle* h, int relative);
+/* perceptual == 3 (more than two zones, zones.py): after apv_begin_block every handle holds the weighting curves of
+ * its own bright zone (zone 0); the dark microphones of handle `dst` that belong to the bright zone of handle `src`
+ * take src's curves (each dark microphone is weighted from its own zone's target: the generalisation of
+ * apvast.py:259-262,318-319).  Device to device, same GPU. */
+int apv_copy_weights(apv_handle* dst, int dst_zone, int dst_mic0, apv_handle* src, int src_zone, int src_mic0, int n_mics);
+
+/* ---- block-range sharding over the GPUs of a box (one process per GPU, NCCL over NVLink bound at run
+ * time with dlopen -- the library links no NCCL symbol).  The reference is one ordered stream of hops
+ * (apvast.py:153-165); its streaming state has finite memory (apvast.py:115-151), so rank g replays S1-S3 over a halo
+ * and owns a contiguous block range; the output overlap-add tail (apvast.py:455-465) is the only data that crosses a
+ * range boundary. */
+int apv_comm_unique_id(void* id128);                                        /* rank 0: ncclGetUniqueId, 128 bytes */
+int apv_comm_init(apv_handle* h, int rank, int nranks, const void* id128);  /* nranks == 1: no communicator needed */
+int apv_comm_destroy(apv_handle* h);
+int apv_nccl_version(int* version);
+/* device buffers for ranges of up to max_halo + max_owned blocks; total_on_root = blocks the gathering rank receives */
+int apv_range_reserve(apv_handle* h, int max_halo, int max_owned, int total_on_root);
+/* n_halo state-only blocks, then n_owned full blocks (pipelined); in_*: (n_halo + n_owned) * H samples, host or device
+ * pointers.  Asynchronous: returns once everything is enqueued; outputs and filters of the owned blocks stay in HBM. */
+int apv_range_run(apv_handle* h, int n_halo, int n_owned, const double* in_A, const double* in_B, int inputs_on_device);
+/* overlap-add halo: G[:, :, H:] of rank g -> rank g+1 (ncclSend/ncclRecv on the handle's stream), added to the first
+ * Nb/H - 1 owned output blocks there.  Every range but the last must hold at least Nb/H - 1 blocks. */
+int apv_range_exchange_halo(apv_handle* h);
+/* outputs (counts[r] blocks of (2, V, H, L)) and filters ((2, V, n)) of every rank, in rank order, into the HBM of
+ * `root` and from there to out_host / w_host (root only, may be NULL; pinned memory recommended: apv_alloc_pinned).
+ * Synchronises; returns the first joint-diagonalisation failure of any block. */
+int apv_range_gather(apv_handle* h, int root, const int* counts, double* out_host, double* w_host);
+int apv_range_device_ptrs(apv_handle* h, void** gathered_out, void** gathered_w, void** own_out, void** own_w);
+/* test hooks: the packed tail this handle would send / adding a tail without a communicator */
+int apv_range_tail_get(apv_handle* h, double* tail_host);
+int apv_range_tail_add(apv_handle* h, const double* tail_host);
+void* apv_alloc_pinned(size_t bytes);
+void apv_free_pinned(void* p);
 
 int apv_get(apv_handle* h, int tensor_id, double* dst, size_t count);
 int apv_set(apv_handle* h, int tensor_id, const double* src, size_t count);
