@@ -68,7 +68,7 @@ class apvast:
                  statistics_buffer_length: int, hop_size: int = None, sampling_rate: int = 48000,
                  run_A: bool = True, run_B: bool = True, perceptual: bool = True, *, model=None,
                  device: int = None, eig_mode: int = 0, stats_mode: int = 0, flavour: str = "python",
-                 fullscale_db: float = 94.0, active_mics_A: int = 0):
+                 fullscale_db: float = 94.0, active_mics_A: int = 0, split_weights: bool = False):
         self._h = None
         if flavour not in ("python", "matlab"):
             raise RuntimeError("flavour must be 'python' or 'matlab'")
@@ -118,7 +118,7 @@ class apvast:
             if model is None:
                 from .perceptual import MaskingModel
                 self.model = MaskingModel(Nb, sampling_rate, fullscale_db)
-                mode = 1
+                mode = 3 if split_weights else 1      # 3: S1 + S2, then weighting curves may be exchanged (zones.py)
             else:
                 self.model = model
                 mode = 2
@@ -146,13 +146,14 @@ class apvast:
         h = C.c_void_p()
         capi.check(capi.lib().apv_create(C.byref(cfg), capi.ptr(rA), capi.ptr(rB), capi.ptr(init), C.byref(h)))
         self._h = h
-        if mode == 1:
+        if mode in (1, 3):
             capi.check(capi.lib().apv_set_gain_table(self._h, self.model.n_channels, capi.ptr(self.model.G2),
                                                      self.model.Cs, self.model.Ca, self.model.Leff))
         self._mode = mode
         self._n = self.filter_length * L
         self._blocks = 0
         self._reg_relative = not EXPERIMENTAL_REGULARIZATION
+        self._between = None       # mode 3: hook called between S2 and S3 (exchange of weighting curves)
 
     def _sync_flags(self):
         # the reference reads EXPERIMENTAL_REGULARIZATION inside jdiag, i.e. at call time (Python/apvast.py:22-27)
@@ -197,9 +198,12 @@ class apvast:
         oBt = np.empty((H, L))
         lib = capi.lib()
         self._sync_flags()
-        if self._mode == 2:
+        if self._mode in (2, 3):
             capi.check(lib.apv_begin_block(self._h, capi.ptr(a), capi.ptr(b)))
-            self._host_gains()
+            if self._mode == 2:
+                self._host_gains()
+            elif self._between is not None:
+                self._between(self)
             capi.check(lib.apv_finish_block(self._h, capi.ptr(oA), capi.ptr(oB), capi.ptr(oAt), capi.ptr(oBt)))
         else:
             capi.check(lib.apv_process_block(self._h, capi.ptr(a), capi.ptr(b), capi.ptr(oA), capi.ptr(oB),
@@ -210,6 +214,26 @@ class apvast:
         out_B = [oB[v] for v in sel] if self.run_B else None
         # the reference returns V identical target arrays (:418,422,467-475,501,504)
         return out_A, out_B, [oAt for _ in sel], [oBt for _ in sel]
+
+    def _begin(self, input_A, input_B):
+        """S1 + S2 of a split block (mode 3); ``_finish`` runs S3..S7."""
+        if np.size(input_A) != self.hop_size or np.size(input_B) != self.hop_size:
+            raise RuntimeError("invalid input size")
+        a = np.ascontiguousarray(input_A, dtype=np.float64).reshape(-1)
+        b = np.ascontiguousarray(input_B, dtype=np.float64).reshape(-1)
+        self._sync_flags()
+        capi.check(capi.lib().apv_begin_block(self._h, capi.ptr(a), capi.ptr(b)))
+
+    def _finish(self):
+        V, H, L = self.number_of_eigenvectors, self.hop_size, self.number_of_srcs
+        oA = np.empty((V, H, L)) if self.run_A else None
+        oB = np.empty((V, H, L)) if self.run_B else None
+        oAt, oBt = np.empty((H, L)), np.empty((H, L))
+        capi.check(capi.lib().apv_finish_block(self._h, capi.ptr(oA), capi.ptr(oB), capi.ptr(oAt), capi.ptr(oBt)))
+        self._blocks += 1
+        sel = range(V) if self._ranks is None else [r - 1 for r in self._ranks]
+        return ([oA[v] for v in sel] if self.run_A else None, [oB[v] for v in sel] if self.run_B else None,
+                [oAt for _ in sel], [oBt for _ in sel])
 
     def _host_gains(self):
         """perceptual with a host model: W[:, m] = model.gain(time block), unit-norm (:313-324)."""
@@ -233,8 +257,8 @@ class apvast:
 
         Returns ``(out_A, out_B, out_A_t, out_B_t[, w])``: arrays (nblocks, V, H, L) (``None`` for a zone that is off),
         (nblocks, H, L) for the target streams, and with ``want_filters`` the per-hop filters (nblocks, 2, V, n)."""
-        if self._mode == 2:
-            raise RuntimeError("process_blocks is not available with a host perceptual model")
+        if self._mode in (2, 3):
+            raise RuntimeError("process_blocks is not available with a split perceptual call")
         a = np.ascontiguousarray(signal_A, dtype=np.float64).reshape(-1)
         b = np.ascontiguousarray(signal_B, dtype=np.float64).reshape(-1)
         H = self.hop_size
@@ -262,8 +286,8 @@ class apvast:
 
     def advance_state(self, input_A, input_B):
         """S1-S3 only (state update without statistics/filters/rendering): warm-up of a block range."""
-        if self._mode == 2:
-            raise RuntimeError("advance_state is not available with a host perceptual model")
+        if self._mode in (2, 3):
+            raise RuntimeError("advance_state is not available with a split perceptual call")
         a = np.ascontiguousarray(input_A, dtype=np.float64).reshape(-1)
         b = np.ascontiguousarray(input_B, dtype=np.float64).reshape(-1)
         if a.size != self.hop_size or b.size != self.hop_size:

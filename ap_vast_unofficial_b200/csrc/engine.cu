@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "engine.cuh"
@@ -221,14 +222,17 @@ bool pipelined(const Handle& h) {
   return h.pipeline != 0 && h.cfg.loading_mode != 1 && !h.cfg.reg_relative && h.cfg.perceptual < 2;
 }
 
-// One block of a multi-block call.  With pipelining the front half (S1-S4) goes to the low-priority stream and fills
-// slot b & 1 of the statistics while the back half (S5-S7) of block b - 1 still runs on the main stream: S4 of
-// block b + 1 depends on the streaming state only (apvast.py:329-364), never on the filters of block b.
-// `b` counts from 0 inside the call; results are written to the device buffers of `sink`.
-int enqueue_block(Handle& h, long b, const double* d_inA, const double* d_inB, const BlockSink& sink, bool state_only) {
+// Multi-block calls run every block in two halves.  With pipelining the front half (S1-S4) goes to the low-priority
+// stream and fills slot b & 1 of the statistics while the back half (S5-S7) of block b - 1 still runs on the main
+// stream: S4 of block b + 1 depends on the streaming state only (apvast.py:329-364), never on the filters of block b.
+// The caller enqueues front(b + 1) BEFORE back(b), so that the few launches of a front half are never stuck behind
+// the ~900 launches of a back half in the host's submission order.  `b` counts from 0 inside the call.
+int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only) {
   const int slot = (int)(b & 1);
   const bool pipe = pipelined(h) && !state_only;
   cudaStream_t main_st = h.st;
+  h.launches_front = 0;
+  const int saved = h.launches;
   h.launches = 0;
   use_slot(h, slot);
   if (pipe) {
@@ -240,21 +244,31 @@ int enqueue_block(Handle& h, long b, const double* d_inA, const double* d_inB, c
     }
     h.st = h.st_front;
   }
+  if (h.dbg_ev && !state_only && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 0], h.st);
   int rc = run_front(h, d_inA, d_inB, false, state_only);
+  if (h.dbg_ev && !state_only && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 1], h.st);
   h.st = main_st;
+  h.launches_front = h.launches;
+  h.launches = saved;
   APV_TRY(rc);
-  if (state_only) {
-    for (int i : {7, 4, 5, 6}) APV_CUDA_TRY(cudaEventRecord(h.ev[i], h.st));
-    return OK;
-  }
-  if (pipe) {
-    APV_CUDA_TRY(cudaEventRecord(h.ev_ready[slot], h.st_front));
-    APV_CUDA_TRY(cudaStreamWaitEvent(main_st, h.ev_ready[slot], 0));
-  }
+  if (pipe) APV_CUDA_TRY(cudaEventRecord(h.ev_ready[slot], h.st_front));
+  return OK;
+}
+
+// Back half of block b; results go to the device buffers of `sink`.
+int enqueue_back(Handle& h, long b, const BlockSink& sink) {
+  const int slot = (int)(b & 1);
+  const bool pipe = pipelined(h);
+  cudaStream_t main_st = h.st;
+  use_slot(h, slot);
+  h.launches = h.launches_front;
+  if (pipe) APV_CUDA_TRY(cudaStreamWaitEvent(main_st, h.ev_ready[slot], 0));
   h.W = sink.W ? sink.W : h.home_W;
   h.d_out = sink.out ? sink.out : h.home_out;
   h.d_out_t = sink.out_t ? sink.out_t : h.home_out_t;
-  rc = run_back(h);
+  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 2], main_st);
+  int rc = run_back(h);
+  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 3], main_st);
   if (rc == OK && sink.info && h.nz > 0)
     rc = cudaMemcpyAsync(sink.info, h.jd.info, (size_t)h.nz * 4 * sizeof(int), cudaMemcpyDeviceToDevice, main_st) == cudaSuccess
              ? OK : fail(ECUDA, "status copy failed");
@@ -575,13 +589,16 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
     }
     if (w_out) memcpy(w_out + (size_t)b * perw, src + 2 * per + 2 * (size_t)D.H, perw * sizeof(double));
   };
+  auto sig_ptr = [&](int X, long b) { return d_sig + (size_t)X * sig + (size_t)b * D.H; };
+  if (rc == OK) rc = enqueue_front(*h, 0, sig_ptr(0, 0), sig_ptr(1, 0), false);
   for (long b = 0; b < nblocks && rc == OK; ++b) {
     const int rs = (int)(b % cap);
     double* slot = h->ring + (size_t)rs * sd;
+    if (b + 1 < nblocks) rc = enqueue_front(*h, b + 1, sig_ptr(0, b + 1), sig_ptr(1, b + 1), false);
     if (b >= cap) cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
     BlockSink sink{slot, slot + 2 * per, slot + 2 * per + 2 * (size_t)D.H,
                    reinterpret_cast<int*>(slot + 2 * per + 2 * (size_t)D.H + perw)};
-    if (rc == OK) rc = enqueue_block(*h, b, d_sig + (size_t)b * D.H, d_sig + sig + (size_t)b * D.H, sink, false);
+    if (rc == OK) rc = enqueue_back(*h, b, sink);
     cu(cudaEventRecord(h->ev_rend[rs], h->st), "record");
     cu(cudaStreamWaitEvent(h->st_copy, h->ev_rend[rs], 0), "wait render");
     cu(cudaMemcpyAsync(h->ring_pin + (size_t)rs * sd, slot, sd * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy), "D2H");
@@ -652,6 +669,32 @@ int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B) {
   APV_TRY(copy_in(*h, in_A, in_B));
   APV_TRY(run_block(*h, h->d_in, h->d_in + h->D.H, false, true));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  return OK;
+}
+
+/* Diagnostic: timeline of the next multi-block call.  apv_debug_timeline(h, nblocks, NULL) arms the recording of four
+ * events per block (front start / front end / back start / back end); a later call with `ms` returns their times in
+ * milliseconds relative to the first one ((nblocks, 4), -1 where nothing was recorded). */
+int apv_debug_timeline(apv_handle* h, int nblocks, float* ms) {
+  if (!h || nblocks < 1) return fail(EINVAL_, "bad argument");
+  DevGuard dg(h->device);
+  if (!ms) {
+    if (h->dbg_ev) {
+      for (int i = 0; i < 4 * h->dbg_cap; ++i) cudaEventDestroy(h->dbg_ev[i]);
+      delete[] h->dbg_ev;
+    }
+    h->dbg_ev = new cudaEvent_t[4 * (size_t)nblocks];
+    h->dbg_cap = nblocks;
+    for (int i = 0; i < 4 * nblocks; ++i) APV_CUDA_TRY(cudaEventCreate(&h->dbg_ev[i]));
+    return OK;
+  }
+  if (!h->dbg_ev) return fail(EINVAL_, "apv_debug_timeline: not armed");
+  APV_CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < 4 * std::min(nblocks, h->dbg_cap); ++i) {
+    float t = -1.f;
+    if (cudaEventElapsedTime(&t, h->dbg_ev[0], h->dbg_ev[i]) != cudaSuccess) { t = -1.f; cudaGetLastError(); }
+    ms[i] = t;
+  }
   return OK;
 }
 

@@ -159,6 +159,9 @@ struct Handle {
   int zones[2] = {0, 1};
   float stage_ms[7] = {};
   int launches = 0;
+  int launches_front = 0;
+  cudaEvent_t* dbg_ev = nullptr;   // APV_PIPE_DEBUG: [dbg_cap][4] front start / front end / back start / back end per block
+  int dbg_cap = 0;    // launches of the front half of the block whose back half runs next (multi-block calls)
   bool began = false;
 };
 
@@ -194,7 +197,8 @@ struct BlockSink {   // device destinations of one block's results (nullptr = th
   int* info;       // [8] status of the joint diagonalisation
 };
 bool pipelined(const Handle& h);
-int enqueue_block(Handle& h, long b, const double* d_inA, const double* d_inB, const BlockSink& sink, bool state_only);
+int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only);
+int enqueue_back(Handle& h, long b, const BlockSink& sink);
 int leave_multiblock(Handle& h);
 int status_from_info(const Handle& h, const int* info, long block);
 int range_alloc(Handle& h, int max_owned, int total_on_root);

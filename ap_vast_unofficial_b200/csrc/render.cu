@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(256) render_kernel(const double* __restrict__ 
                                                      int Je, int ncls) {
   extern __shared__ __align__(16) double sm[];
   const int Nb = D.Nb, J = D.J, H = D.H, L = D.L;
-  const int XS = RT + Je - 1 + 1;                 // padded length of one class window
+  const int XS = (RT + Je + 1) & ~1;              // padded (even) length of one class window
   double* tr = sm;                                // [LC][Je]   tr[l][k'] = w[l][Je-1-k']
-  double* xe = tr + (size_t)LC * Je;              // [ncls][XS] xe[c][t] = xw[(h0 + c H + t - (Je-1)) mod Nb]
+  double* xe = tr + (((size_t)LC * Je + 1) & ~(size_t)1);   // even offsets: the output tile is read as double2              // [ncls][XS] xe[c][t] = xw[(h0 + c H + t - (Je-1)) mod Nb]
   double* ot = xe + (size_t)ncls * XS;            // [RT][L]    output tile
   const int h0 = blockIdx.x * RT, v = blockIdx.y, zone = blockIdx.z == 0 ? zone0 : zone1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,7 +185,7 @@ int stage_render(Handle& h) {
     RenderPlan rp;
     rp.Je = std::min(D.J, D.Nb);
     rp.ncls = ceil_div(D.Nb, D.H);
-    const size_t fixed = ((size_t)rp.ncls * (RT + rp.Je) + (size_t)RT * D.L) * sizeof(double);
+    const size_t fixed = ((size_t)rp.ncls * ((RT + rp.Je + 1) & ~1) + (size_t)RT * D.L + 2) * sizeof(double);
     rp.LC = D.L;
     while (rp.LC > 2 && fixed + (size_t)rp.LC * rp.Je * sizeof(double) > 160 * 1024) rp.LC = (rp.LC + 1) / 2;
     rp.LC = std::max(2, (rp.LC + 1) & ~1);       // warps work on loudspeaker pairs

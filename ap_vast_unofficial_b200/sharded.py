@@ -150,7 +150,7 @@ def process_signal_device(make_engine, signal_A, signal_B, rank: int = 0, world:
 
 # ------------------------------------------------------------------------------------------------ generic path
 def process_signal_sharded(make_engine, signal_A, signal_B, rank: int = 0, world: int = 1, dist=None, seed=0,
-                           keep_outputs=True):
+                           keep_outputs=True, gather=True):
     """Run the whole signal, block-range sharded, through the reference's Python interface.  Returns on every rank
     a dict with this rank's ``blocks`` (t0, t1), ``w_A``/``w_B`` lists (one (V, n) array per owned block) and
     ``out_A``/``out_B`` lists ((V, H, L) per owned block, halo already applied); on rank 0 additionally
@@ -217,7 +217,7 @@ def process_signal_sharded(make_engine, signal_A, signal_B, rank: int = 0, world
                         seg = tail[z][:, k * H:(k + 1) * H, :]
                         res[key][k][:, :seg.shape[1], :] += seg
         # ---- final gather of the filters: to rank 0 only (point to point; nobody else needs them)
-        for key in ("w_A", "w_B"):
+        for key in ("w_A", "w_B") if gather else ():
             mine = [w for w in res[key] if w is not None]
             if rank == 0:
                 parts = [mine]

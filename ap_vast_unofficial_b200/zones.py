@@ -10,8 +10,12 @@ second zone holds the microphones of all the other zones.  One two-zone engine p
 whole job on the GPU, unchanged: zone A = zone z (padded with silent microphones to the common count, which the
 statistics skip: ``active_mics_A``), zone B = the union of the other zones, ``run_B=False``.  The loudspeaker signal of the array is the sum of the zones' feeds.
 
-Per-zone perceptual weighting (each dark microphone weighted from its own zone's target) needs one target signal per
-microphone group and is not expressible in this composition: ``perceptual=False`` only.
+Per-zone perceptual weighting (``perceptual=True``): every microphone is weighted with the masking curve derived from
+the target signal of ITS OWN zone -- the generalisation of ``apvast.py:259-262,318-319``, where zone-A microphones use
+W_A (from target A->A) and zone-B microphones W_B (from target B->B).  Engine z computes the curves of its bright
+microphones in S2; the dark microphones of engine z that belong to zone q take engine q's curves.  The engines
+therefore run the block in two halves (``perceptual`` mode 3 of the C-ABI): S1 + S2 on all engines, a device-to-device
+exchange of the weighting curves between the engines (``apv_copy_weights``), then S3..S7.
 """
 from __future__ import annotations
 
@@ -33,8 +37,7 @@ class apvast_zones:
             raise RuntimeError("at least two zones")
         if any(r.shape != rirs[0].shape for r in rirs):
             raise RuntimeError("rirs of unequal size")
-        if engine_kwargs.pop("perceptual", False):
-            raise NotImplementedError("per-zone perceptual weighting is not available for more than two zones")
+        self.perceptual = bool(engine_kwargs.pop("perceptual", False))
         K, L, M = rirs[0].shape
         Z = len(rirs)
         self.n_zones, self.number_of_eigenvectors = Z, int(number_of_eigenvectors)
@@ -44,14 +47,30 @@ class apvast_zones:
             dark = np.concatenate([rirs[q] for q in range(Z) if q != z], axis=2)
             self.engines.append(apvast(block_size, bright, dark, filter_length, modeling_delay, reference_indices[z], 0,
                                        number_of_eigenvectors, mu, statistics_buffer_length, hop_size, sampling_rate,
-                                       run_A=True, run_B=False, perceptual=False, active_mics_A=M, **engine_kwargs))
+                                       run_A=True, run_B=False, perceptual=self.perceptual, split_weights=self.perceptual,
+                                       active_mics_A=M, **engine_kwargs))
         self.hop_size = self.engines[0].hop_size
         self._silence = np.zeros(self.hop_size)
+        self._M = M
+
+    def _exchange_weights(self):
+        from . import _capi as capi
+        lib = capi.lib()
+        Z, M = self.n_zones, self._M
+        for z in range(Z):
+            others = [q for q in range(Z) if q != z]
+            for i, q in enumerate(others):      # dark microphones [i M, (i+1) M) of engine z are zone q's microphones
+                capi.check(lib.apv_copy_weights(self.engines[z]._h, 1, i * M, self.engines[q]._h, 0, 0, M))
 
     def process_input_buffers(self, inputs):
         if len(inputs) != self.n_zones:
             raise RuntimeError("invalid input size")
-        return [eng.process_input_buffers(x, self._silence)[0] for eng, x in zip(self.engines, inputs)]
+        if not self.perceptual:
+            return [eng.process_input_buffers(x, self._silence)[0] for eng, x in zip(self.engines, inputs)]
+        for eng, x in zip(self.engines, inputs):
+            eng._begin(x, self._silence)
+        self._exchange_weights()
+        return [eng._finish()[0] for eng in self.engines]
 
     @property
     def w(self):

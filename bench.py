@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the AP-VAST per-block hot path (BASELINE.json metric: filter updates/sec & real-time factor).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg4|cfg5] [--impl ours|reference]
 
 A *step* is one filter update (one ``process_input_buffers`` call = S1..S7 over one hop of both programme
 signals) per rank.  The workload is BASELINE.json ``configs[2]`` (L=16, J=256, n=4096 -- the configuration the
-north-star target is quoted on; it fits one GPU); ``--workload cfg2`` selects ``configs[1]``.  At N > 1 the
-60-s signal is block-range sharded: every rank owns a contiguous range and processes its own blocks with no
-collective on the per-block path (weak scaling: per-rank work is fixed).
+north-star target is quoted on; it fits one GPU); ``--workload cfg2`` selects ``configs[1]``, ``cfg4`` the mu x V
+sweep at full rank, ``cfg5`` the four-zone n=8192 clips.
+
+What is timed (cfg2 / cfg3), at every N: the block-range-sharded pipeline of SURVEY 8e.  The signal has N*K blocks;
+rank g owns blocks [gK, (g+1)K).  Inside the timed region every rank (1) replays S1-S3 over its halo of
+``warmup_blocks`` blocks (``apv_range_run``, state only), (2) processes its K owned blocks through the pipelined
+multi-block path, (3) exchanges the output overlap-add tail with its neighbours (``apv_range_exchange_halo``:
+ncclSend/ncclRecv over NVLink, device to device), (4) takes part in the gather of all outputs and filters into
+rank 0's HBM (``apv_range_gather``).  Weak scaling: per-rank work is fixed.  After the timed regions rank 0 runs block
+K (the first block of rank 1) in its own single stream and asserts that the stitched result equals it to <= 1e-8.
 
 Printed JSON line (rank 0):
-  value     whole-job filter updates/s with the step inputs already resident in HBM (device-timed, CUDA
-            events on the engine's stream, max over ranks)
-  e2e       the same metric through the public drop-in call ``apvast.process_input_buffers`` with HOST
-            buffers: pinned H2D of the hop and D2H of the rendered outputs inside the timed region
-  roofline  the dominant kernel.  At cfg3 (n >= 2048: two-stage tridiagonalisation) that is the FP64 tensor-core
-            statistics SYRK: algorithmic flops per block / its launch duration against the DMMA peak measured
-            live in this process (MEASURED_PEAKS.json has no FP64 figure).  At cfg2 (one-stage tridiagonalisation)
-            it is td_panel_kernel against MEASURED_PEAKS.json hbm_gbs.
-  roofline_tridiag / roofline_stats   the other of the two
+  value     whole-job filter updates/s, hops resident in HBM when the timed region starts, gathered results left in
+            rank 0's HBM; CUDA events on the engine's stream, max over ranks
+  e2e       the same pipeline with HOST buffers: pinned-free H2D of the hops inside the timed region and D2H of all
+            gathered outputs + filters into pinned host memory on rank 0
+  e2e_per_call / e2e_batched (N=1)   the drop-in per-hop loop ``apvast.process_input_buffers`` and the multi-hop
+            call ``apvast.process_blocks`` (apv_process_blocks), host buffers in and out
+  roofline  the dominant kernel, the FP64 tensor-core statistics SYRK: algorithmic flops per block / its launch
+            duration (CUDA events around its launches, in a sequential section where it does not share the SMs with
+            the joint diagonalisation of the previous block) against the DMMA peak measured live in this process
+  roofline_tridiag, roofline_render, roofline_wola, roofline_sweep   the other kernels (FP64 tensor / HBM GB/s)
   cpu_baseline     the oracle port of the reference timed on this box's host cores on a bounded sample
 
 ``--impl reference`` times the reference algorithm's CPU implementation (the oracle port: /root/reference is
@@ -26,12 +34,19 @@ not on the GPU box and the reference is pure NumPy/SciPy) on the host cores.
 """
 from __future__ import annotations
 
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers when nproc > 1; the reference arm is a CPU
+    # measurement on ALL host cores, so the BLAS pool is sized before NumPy loads (and again with threadpoolctl below)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import argparse
 import ctypes as C
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -51,6 +66,25 @@ def _peaks():
             d = json.load(f)
         return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_profile():
+    """Figures that only a profiler can give (DRAM traffic, pipe utilisation), read from the committed capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_syrk.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def workload_config(args, sh, world):
+    """The `config` object of the JSON line: identical for both arms."""
+    return {"workload": f"{args.workload}: synthetic 2-zone L={sh['L']} M={sh['M']} J={sh['J']} n={sh['n']} "
+                        f"K={sh['K']} Nb={sh['Nb']} H={sh['H']} N={sh['N']} V={sh['V']} fs=48000",
+            "sharding": f"contiguous block ranges over {world} rank(s): S1-S3 halo replay, overlap-add tail "
+                        f"ncclSend/ncclRecv, gather to rank 0",
+            "l2": "per-block working set ~1.6 GB (4 R + jdiag workspace) >> 126 MB L2; no explicit flush"}
 
 
 class ClockSampler:
@@ -102,72 +136,73 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(wl, n_timed, n_state_warm, mics_sample=2, verbose=False):
-    """Time the oracle port of the reference on a bounded sample of the workload.
-
-    Per timed step: S1-S3, S6, S7 in full; S4 on `mics_sample` of the M microphones (cost is exactly linear in
-    the microphones: apvast.py:332-364 loops over m) and S5 on ONE of the two zones (the two jdiag calls,
-    apvast.py:380-382, are identical in cost).  Step time = S123 + S4_sample * M/mics_sample + 2 * S5_sample + S67.
-    Returns (seconds per block list, per-stage split of the last step)."""
-    import scipy.linalg as sla
+def _oracle_engine(wl):
     from oracle import apvast_oracle as ora
-    cfg = wl["cfg"]
     np.random.seed(0)
-    eng = ora.ApvastOracle(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **cfg)
-    H = eng.hop_size
+    return ora, ora.ApvastOracle(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **wl["cfg"])
+
+
+def _spin_blas():
+    w = np.random.default_rng(0).standard_normal((512, 512))
+    for _ in range(3):                      # spin up the BLAS thread pool before anything is timed
+        _ = w @ w.T
+
+
+def cpu_full_step(eng, a, b):
+    """One un-sampled block of the oracle port: all microphones, both zones (apvast.py:153-165)."""
+    t0 = time.perf_counter()
+    eng.process_input_buffers(a, b)
+    return time.perf_counter() - t0
+
+
+def cpu_sampled_step(ora, eng, a, b, pencil, mics_sample=2):
+    """One block on a bounded sample.  S1-S3, S6, S7 in full; S4 on `mics_sample` of the M microphones (its cost is
+    exactly linear in the microphones: apvast.py:332-364 loops over m) and S5 on ONE of the two zones (the two jdiag
+    calls, apvast.py:380-382, cost the same), on `pencil` = (R_B, R_D) of a block computed with ALL microphones.
+    Step time = S123 + S4_sample * M/mics_sample + 2 * S5_sample + S67."""
     M = eng.number_of_mics
     ms = min(mics_sample, M)
     J, V, mu = eng.filter_length, eng.number_of_eigenvectors, eng.mu
-    t_blk = 0
-    _w = np.random.default_rng(0).standard_normal((512, 512))
-    for _ in range(3):                      # spin up the BLAS thread pool before anything is timed
-        _ = _w @ _w.T
-    for _ in range(n_state_warm):           # fill the statistics buffers (state only, untimed)
-        eng.advance_state(wl["signal_A"][t_blk * H:(t_blk + 1) * H], wl["signal_B"][t_blk * H:(t_blk + 1) * H])
-        t_blk += 1
-    times, split = [], {}
-    for _ in range(n_timed):
-        a = wl["signal_A"][t_blk * H:(t_blk + 1) * H]; b = wl["signal_B"][t_blk * H:(t_blk + 1) * H]
-        t_blk += 1
-        t0 = time.perf_counter()
-        eng.update_loudspeaker_response_buffers(a, b)
-        eng.update_weighted_target_signals()
-        eng.update_weighted_loudspeaker_response()
-        t1 = time.perf_counter()
-        # S4 sample: zone-A bright/dark + zone-B bright/dark for `ms` microphones
-        n = J * eng.number_of_srcs
-        R = [np.zeros((n, n)) for _ in range(4)]
-        r = [np.zeros((n, 1)) for _ in range(2)]
-        for m in range(ms):
-            Y = eng._data_matrix(eng.loudspeaker_weighted_response_A_to_A_buffer, m); R[0] += Y @ Y.T
-            r[0] += Y @ eng.loudspeaker_weighted_target_response_A_to_A_buffer[J:, m].reshape(-1, 1)
-            Y = eng._data_matrix(eng.loudspeaker_weighted_response_A_to_B_buffer, m); R[1] += Y @ Y.T
-            Y = eng._data_matrix(eng.loudspeaker_weighted_response_B_to_B_buffer, m); R[3] += Y @ Y.T
-            r[1] += Y @ eng.loudspeaker_weighted_target_response_B_to_B_buffer[J:, m].reshape(-1, 1)
-            Y = eng._data_matrix(eng.loudspeaker_weighted_response_B_to_A_buffer, m); R[2] += Y @ Y.T
-        t2 = time.perf_counter()
-        # S5 sample: one zone (regularised a little more because the sampled R_D has fewer microphones)
-        U, D = ora.jdiag(R[0], R[1] + 1e-9 * np.trace(R[1]) / n * np.eye(n))
-        t3 = time.perf_counter()
-        lam = np.diag(D)
-        c = U[:, :V].T @ r[0].reshape(-1)
-        w = np.cumsum((c / (lam[:V] + mu))[None, :] * U[:, :V], axis=1).T.reshape(V, n, 1)
-        eng.w_A = w; eng.w_B = w
-        L, Nb = eng.number_of_srcs, eng.block_size
-        eng.filter_spectra_A = [np.fft.rfft(w[v, :, 0].reshape(L, J).T, Nb, axis=0) for v in range(V)]
-        eng.filter_spectra_B = eng.filter_spectra_A
-        ft = np.zeros(n); ft[J * eng.reference_index_A + eng.modeling_delay] = 1.0
-        ftf = np.fft.rfft(ft.reshape(L, J).T, Nb, axis=0)
-        eng.filter_spectra_A_t = [ftf] * V; eng.filter_spectra_B_t = [ftf] * V
-        eng.update_input_blocks(a, b)
-        eng.compute_output_buffers()
-        t4 = time.perf_counter()
-        s123, s4, s5, s67 = t1 - t0, (t2 - t1) * (M / ms), 2.0 * (t3 - t2), t4 - t3
-        times.append(s123 + s4 + s5 + s67)
-        split = {"S1S2S3": s123, "S4_scaled": s4, "S5_scaled": s5, "S6S7": s67, "sample_wall_s": t4 - t0}
-        if verbose:
-            print("cpu sample", split, file=sys.stderr)
-    return times, split, f"per step: S1-S3,S6,S7 full; S4 on {ms}/{M} mics x{M / ms:g}; S5 (jdiag, n={n}) on 1/2 zones x2"
+    L, Nb = eng.number_of_srcs, eng.block_size
+    n = J * L
+    t0 = time.perf_counter()
+    eng.update_loudspeaker_response_buffers(a, b)
+    eng.update_weighted_target_signals()
+    eng.update_weighted_loudspeaker_response()
+    t1 = time.perf_counter()
+    R = [np.zeros((n, n)) for _ in range(4)]
+    r = [np.zeros((n, 1)) for _ in range(2)]
+    for m in range(ms):
+        Y = eng._data_matrix(eng.loudspeaker_weighted_response_A_to_A_buffer, m); R[0] += Y @ Y.T
+        r[0] += Y @ eng.loudspeaker_weighted_target_response_A_to_A_buffer[J:, m].reshape(-1, 1)
+        Y = eng._data_matrix(eng.loudspeaker_weighted_response_A_to_B_buffer, m); R[1] += Y @ Y.T
+        Y = eng._data_matrix(eng.loudspeaker_weighted_response_B_to_B_buffer, m); R[3] += Y @ Y.T
+        r[1] += Y @ eng.loudspeaker_weighted_target_response_B_to_B_buffer[J:, m].reshape(-1, 1)
+        Y = eng._data_matrix(eng.loudspeaker_weighted_response_B_to_A_buffer, m); R[2] += Y @ Y.T
+    t2 = time.perf_counter()
+    U, D = ora.jdiag(pencil[0], pencil[1])
+    t3 = time.perf_counter()
+    lam = np.diag(D)
+    c = U[:, :V].T @ r[0].reshape(-1)
+    w = np.cumsum((c / (lam[:V] + mu))[None, :] * U[:, :V], axis=1).T.reshape(V, n, 1)
+    eng.w_A = w; eng.w_B = w
+    eng.filter_spectra_A = [np.fft.rfft(w[v, :, 0].reshape(L, J).T, Nb, axis=0) for v in range(V)]
+    eng.filter_spectra_B = eng.filter_spectra_A
+    ft = np.zeros(n); ft[J * eng.reference_index_A + eng.modeling_delay] = 1.0
+    ftf = np.fft.rfft(ft.reshape(L, J).T, Nb, axis=0)
+    eng.filter_spectra_A_t = [ftf] * V; eng.filter_spectra_B_t = [ftf] * V
+    eng.update_input_blocks(a, b)
+    eng.compute_output_buffers()
+    t4 = time.perf_counter()
+    s123, s4, s5, s67 = t1 - t0, (t2 - t1) * (M / ms), 2.0 * (t3 - t2), t4 - t3
+    split = {"S1S2S3": s123, "S4_scaled": s4, "S5_scaled": s5, "S6S7": s67, "sample_wall_s": t4 - t0}
+    return s123 + s4 + s5 + s67, split
+
+
+def sample_text(eng, ms=2):
+    M, n = eng.number_of_mics, eng.filter_length * eng.number_of_srcs
+    return (f"S1-S3,S6,S7 full; S4 on {min(ms, M)}/{M} mics x{M / min(ms, M):g}; S5 (jdiag, n={n}, the pencil of a block "
+            f"with all microphones) on 1/2 zones x2")
 
 
 def blas_threads():
@@ -178,229 +213,358 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def cpu_baseline_leg(workload, budget_s=30.0):
+    """`cpu_baseline` of the GPU arm's line: one sampled step (~10-30 s of CPU work) after a state warm-up.  The pencil
+    of the S5 sample comes from a statistics update with all microphones, run once outside the timed step."""
+    from ap_vast_unofficial_b200.workloads import make_workload
+    wl = make_workload(workload, n_blocks=8)
+    ora, eng = _oracle_engine(wl)
+    H = eng.hop_size
+    _spin_blas()
+    for t in range(4):
+        eng.advance_state(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+    eng.update_statistics()
+    pencil = (eng.R_A_to_A.copy(), eng.R_A_to_B.copy())
+    sec, split = cpu_sampled_step(ora, eng, wl["signal_A"][4 * H:5 * H], wl["signal_B"][4 * H:5 * H], pencil)
+    return {"value": 1.0 / sec, "unit": "updates/s", "cores": blas_threads(), "kind": "port", "extrapolated": True,
+            "sample": "one step: " + sample_text(eng), "split_s": split, "host_cpus": os.cpu_count()}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     from ap_vast_unofficial_b200.workloads import make_workload
-    wl = make_workload(args.workload, n_blocks=args.steps + args.warmup + 4)
+    t_start = time.perf_counter()
+    budget_s = float(os.environ.get("APV_REF_BUDGET_S", "600"))
+    n_warm = max(args.warmup, 4)
+    wl = make_workload(args.workload, n_blocks=args.steps + n_warm + 2)
     sh = wl["shapes"]
-    t0 = time.perf_counter()
-    # warm-up steps only advance the state (there is nothing to warm on the CPU besides filling the buffers)
-    times, split, sample = cpu_reference_sample(wl, args.steps, max(args.warmup, 3))
+    ora, eng = _oracle_engine(wl)
+    H = eng.hop_size
+    _spin_blas()
+    blk = 0
+    for _ in range(n_warm):                  # warm-up steps: state only (fills the statistics buffers), untimed
+        eng.advance_state(wl["signal_A"][blk * H:(blk + 1) * H], wl["signal_B"][blk * H:(blk + 1) * H])
+        blk += 1
+    # the first steps run UN-SAMPLED (all microphones, both zones, the workload's own pencil); at cfg-2 sizes every step does
+    n_full = args.steps if sh["n"] <= 1024 else min(2, args.steps)
+    times, full_times, samp_times, split = [], [], [], {}
+    for _ in range(n_full):
+        dt = cpu_full_step(eng, wl["signal_A"][blk * H:(blk + 1) * H], wl["signal_B"][blk * H:(blk + 1) * H])
+        blk += 1
+        times.append(dt); full_times.append(dt)
+        print("reference arm: full step %.1f s" % dt, file=sys.stderr, flush=True)
+    pencil = (eng.R_A_to_A.copy(), eng.R_A_to_B.copy()) if n_full < args.steps else None
+    executed = n_full
+    for i in range(n_full, args.steps):
+        elapsed = time.perf_counter() - t_start
+        per = float(np.mean([s["sample_wall_s"] for s in [split]])) if split else 25.0
+        if elapsed + per > budget_s:         # keep the whole arm inside the driver's per-N limit
+            break
+        dt, split = cpu_sampled_step(ora, eng, wl["signal_A"][blk * H:(blk + 1) * H], wl["signal_B"][blk * H:(blk + 1) * H], pencil)
+        blk += 1
+        times.append(dt); samp_times.append(dt)
+        executed += 1
+    if executed < args.steps:                # the remaining steps carry the mean of the sampled ones
+        fill = float(np.mean(samp_times)) if samp_times else float(np.mean(times))
+        times += [fill] * (args.steps - executed)
     sec = float(np.mean(times))
     ups = 1.0 / sec
+    validation = None
+    if full_times and samp_times:
+        f, e = float(np.mean(full_times)), float(np.mean(samp_times))
+        validation = {"full_ms": f * 1e3, "extrapolated_ms": e * 1e3, "rel_diff": (e - f) / f,
+                      "full_steps": len(full_times), "sampled_steps": len(samp_times)}
     line = {
         "impl": "reference", "metric": "filter_updates_per_sec", "value": ups, "unit": "updates/s",
         "rtf": ups * sh["H"] / FS, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: synthetic 2-zone L={sh['L']} M={sh['M']} J={sh['J']} n={sh['n']} "
-                               f"K={sh['K']} Nb={sh['Nb']} H={sh['H']} N={sh['N']} V={sh['V']} fs=48000"},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, sh, max(world, args.gpus)),
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": blas_threads(), "kind": "port",
-                         "sample": sample, "split_s": split, "host_cpus": os.cpu_count()},
+                         "extrapolated": bool(samp_times) or executed < args.steps,
+                         "sample": f"{len(full_times)} step(s) un-sampled (all microphones, both zones); "
+                                   f"{len(samp_times)} step(s) sampled: " + sample_text(eng)
+                                   + (f"; {args.steps - executed} step(s) not executed (time budget), filled with the mean"
+                                      if executed < args.steps else ""),
+                         "split_s": split, "host_cpus": os.cpu_count(), "steps_executed": executed},
+        "sample_validation": validation,
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from ap_vast_unofficial_b200 import _capi as capi
     from ap_vast_unofficial_b200 import apvast
-    from ap_vast_unofficial_b200.sharded import block_ranges
+    from ap_vast_unofficial_b200.sharded import RangeRunner
     from ap_vast_unofficial_b200.workloads import make_workload
 
     dist = None
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist_mod
-        torch.cuda.set_device(local_rank)
         dist_mod.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
         dist = dist_mod
-    else:
-        torch.cuda.set_device(local_rank)
     lib = capi.lib()
     K, W = args.steps, args.warmup
-    # each rank owns a contiguous block range of the 60-s signal; it only needs its own samples
-    full = make_workload(args.workload, n_blocks=None)
-    nblk_total = full["n_blocks"]
+    # the signal: world * K blocks (rank g owns [gK, (g+1)K)) + one more block for the boundary check on rank 0
+    full = make_workload(args.workload, n_blocks=world * K + 1)
     sh = full["shapes"]
-    H = sh["H"]
-    t0, t1 = block_ranges(nblk_total, world)[rank]
-    need = W + 2 * K + 3
-    start = min(t0, max(0, nblk_total - need))
-    sigA = full["signal_A"][start * H:(start + need) * H]
-    sigB = full["signal_B"][start * H:(start + need) * H]
+    H, V, L, n = sh["H"], sh["V"], sh["L"], sh["n"]
     np.random.seed(0)
     eng = apvast(rir_A=full["rir_A"], rir_B=full["rir_B"], perceptual=False, device=local_rank, **full["cfg"])
-    V, L, n = sh["V"], sh["L"], sh["n"]
+    if args.no_pipeline:
+        eng.set_pipeline(False)
+    rr = RangeRunner(eng, rank, world, dist, max_owned=max(K, W), total_blocks=world * max(K, W))
+    t0 = rank * K
+    n_halo = min(rr.halo, t0)
+    start = t0 - n_halo
+    sigA = np.ascontiguousarray(full["signal_A"][start * H:(t0 + K + 1) * H])
+    sigB = np.ascontiguousarray(full["signal_B"][start * H:(t0 + K + 1) * H])
+    nb_range = n_halo + K
+    state0 = eng.get_state()                   # the seeded start of the stream (rank 0: the reference's randn buffers)
 
-    # device-resident inputs for the kernel-only measurement
-    d_sig = torch.from_numpy(np.stack([sigA, sigB])).cuda()
+    d_sig = torch.from_numpy(np.stack([sigA, sigB])).cuda()     # hops resident in HBM for the device-timed region
     torch.cuda.synchronize()
-
-    def dev_ptr(sig, blk):
-        return C.c_void_p(d_sig.data_ptr() + (sig * d_sig.shape[1] + blk * H) * 8)
+    ptrA, ptrB = d_sig.data_ptr(), d_sig.data_ptr() + d_sig.shape[1] * 8
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    blk = 0
-    # ---- warm-up (untimed): fills the statistics buffers and warms clocks / instruction caches
-    for _ in range(W):
-        capi.check(lib.apv_process_block_device(eng._h, dev_ptr(0, blk), dev_ptr(1, blk)))
-        blk += 1
-    capi.check(lib.apv_synchronize(eng._h))
+    counts = [K] * world
+    per_out, per_w = 2 * V * H * L, 2 * V * n
+    out_host = capi.pinned_array((world * K, 2, V, H, L)) if rank == 0 else None
+    w_host = capi.pinned_array((world * K, 2, V, n)) if rank == 0 else None
+
+    # ---- warm-up (untimed): W blocks through the same sharded pipeline (kernels, NCCL channels, clocks)
+    Wb = min(W, K)
+    rr.run(None, None, n_halo, Wb, device_ptrs=(ptrA, ptrB))
+    rr.exchange_halo()
+    rr.gather([Wb] * world, None, None)
+    eng.set_state(state0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- timed region 1: K steps, inputs resident in HBM, CUDA events on the engine's stream
+
+    # ---- timed region 1: hops resident in HBM, gathered results stay in rank 0's HBM; CUDA events on the engine's stream
     barrier()
     capi.check(lib.apv_timer_start(eng._h))
-    launches = 0
-    kt_panel, kt_syrk = 0.0, 0.0
-    stage_acc = {}
-    for _ in range(K):
-        capi.check(lib.apv_process_block_device(eng._h, dev_ptr(0, blk), dev_ptr(1, blk)))
-        blk += 1
-        launches += int(lib.apv_launch_count(eng._h))
+    rr.run(None, None, n_halo, K, device_ptrs=(ptrA, ptrB))
+    launches_block = int(lib.apv_launch_count(eng._h))
+    rr.exchange_halo()
+    rr.gather(counts, None, None)
     ms = C.c_float(0)
     capi.check(lib.apv_timer_stop(eng._h, C.byref(ms)))
     barrier()
     dev_ms = float(ms.value)
-    # per-kernel times of the LAST timed block (events recorded inside the timed region)
-    kt = (C.c_float * 4)()
-    capi.check(lib.apv_kernel_times(eng._h, kt))
-    kt_panel, kt_syrk, n_panel = float(kt[0]), float(kt[1]), int(kt[2])
-    stage_acc = eng.stage_times()
+    kt_pipe = (C.c_float * 4)()
+    capi.check(lib.apv_kernel_times(eng._h, kt_pipe))
+    stage_pipe = eng.stage_times()
 
-    # ---- timed region 2: end to end through the drop-in call, host buffers in, host buffers out
-    # (one untimed call first: the host path's pinned staging buffer is allocated on first use)
-    eng.process_input_buffers(sigA[blk * H:(blk + 1) * H], sigB[blk * H:(blk + 1) * H])
-    blk += 1
+    # ---- timed region 2: end to end, HOST buffers in, pinned host buffers out on rank 0
+    eng.set_state(state0)
     barrier()
     te0 = time.perf_counter()
-    chk = 0.0
-    trace = []
-    for _ in range(K):
-        tc0 = time.perf_counter()
-        oA, oB, oAt, oBt = eng.process_input_buffers(sigA[blk * H:(blk + 1) * H], sigB[blk * H:(blk + 1) * H])
-        chk += float(oA[0][0, 0])
-        blk += 1
-        trace.append(1e3 * (time.perf_counter() - tc0))
-    if os.environ.get("APV_BENCH_TRACE"):
-        print("e2e per-call ms:", " ".join("%.1f" % x for x in trace), file=sys.stderr, flush=True)
-    torch.cuda.synchronize()
+    rr.run(sigA[:nb_range * H], sigB[:nb_range * H], n_halo, K)
+    rr.exchange_halo()
+    rr.gather(counts, out_host, w_host)
     e2e_s = time.perf_counter() - te0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-
-    # ---- alternative configuration (not the headline): statistics by the structured evaluation (stats_mode=2)
-    alt = None
-    if not args.no_alt:
-        np.random.seed(0)
-        eng2 = apvast(rir_A=full["rir_A"], rir_B=full["rir_B"], perceptual=False, device=local_rank, stats_mode=2,
-                      **full["cfg"])
-        b2 = 0
-        for _ in range(W):
-            capi.check(lib.apv_process_block_device(eng2._h, dev_ptr(0, b2), dev_ptr(1, b2)))
-            b2 += 1
-        capi.check(lib.apv_synchronize(eng2._h))
-        barrier()
-        capi.check(lib.apv_timer_start(eng2._h))
-        for _ in range(K):
-            capi.check(lib.apv_process_block_device(eng2._h, dev_ptr(0, b2), dev_ptr(1, b2)))
-            b2 += 1
-        ms2 = C.c_float(0)
-        capi.check(lib.apv_timer_stop(eng2._h, C.byref(ms2)))
-        barrier()
-        alt_ms = torch.tensor([float(ms2.value)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(alt_ms, op=dist.ReduceOp.MAX)
-        st2 = eng2.stage_times()
-        alt = {"what": "same workload with stats_mode=2 (first-row correlations + double-double diagonal recurrence "
-                       "instead of the DMMA SYRK; identical parity, ~J/2 x fewer flops); device-timed like `value`",
-               "value": world * K / (float(alt_ms[0].item()) * 1e-3), "unit": "updates/s",
-               "ms_per_step": float(alt_ms[0].item()) / K, "S4_stats_ms": st2["S4_stats"]}
-        eng2.close()
 
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t_dev[0].item()), float(t_dev[1].item())
 
+    # ---- boundary check: rank 0 continues ITS stream with block K = the first block of rank 1
+    boundary = None
     if rank == 0:
-        hbm_peak, peak_src = _peaks()
-        nz = 2
-        # algorithmic bytes of the tridiagonalisation per block: the trailing matrix is read once per column
-        # (n^3/3 * 8 B per zone), both zones
+        oA, oB, _, _ = eng.process_input_buffers(sigA[K * H:(K + 1) * H], sigB[K * H:(K + 1) * H])
+        if world > 1:
+            got_out, got_w = out_host[K], w_host[K]
+            boundary = {"block": K, "out_A_rel": _rel(got_out[0], np.stack(oA)), "out_B_rel": _rel(got_out[1], np.stack(oB)),
+                        "w_A_rel": max(_rel(got_w[0][v], eng.w_A[v, :, 0]) for v in range(V)),
+                        "w_B_rel": max(_rel(got_w[1][v], eng.w_B[v, :, 0]) for v in range(V)), "bar": 1e-8}
+            assert max(boundary["out_A_rel"], boundary["out_B_rel"], boundary["w_A_rel"], boundary["w_B_rel"]) <= 1e-8, boundary
+        chk = float(out_host[0, 0, 0, 0, 0])
+
+    if rank != 0:
+        rr.close(); eng.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # =============================== rank 0 only from here: per-kernel figures, single-GPU extras, the JSON line
+    # sequential section: blocks strictly one after the other on one stream, so that the CUDA events around a kernel
+    # measure that kernel alone (in the pipelined regions S4 of block t+1 shares the SMs with S5 of block t)
+    Kr = max(2, min(K, 4))
+    for i in range(Kr):
+        capi.check(lib.apv_process_block_device(eng._h, C.c_void_p(ptrA + i * H * 8), C.c_void_p(ptrB + i * H * 8)))
+    capi.check(lib.apv_synchronize(eng._h))
+    kt = (C.c_float * 4)()
+    capi.check(lib.apv_kernel_times(eng._h, kt))
+    kt_panel, kt_syrk, n_panel = float(kt[0]), float(kt[1]), int(kt[2])
+    stage_seq = eng.stage_times()
+
+    extras = {}
+    if world == 1:
+        # the drop-in per-hop loop (the reference's own calling convention) and the multi-hop call, host buffers
+        eng.set_state(state0)
+        eng.process_input_buffers(sigA[:H], sigB[:H])
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        for i in range(1, K + 1):
+            eng.process_input_buffers(sigA[i * H:(i + 1) * H], sigB[i * H:(i + 1) * H])
+        percall_s = time.perf_counter() - tp0
+        eng.set_state(state0)
+        eng.process_blocks(sigA[:2 * H], sigB[:2 * H])                          # allocates the rings
+        eng.set_state(state0)
+        tb0 = time.perf_counter()
+        eng.process_blocks(sigA[:K * H], sigB[:K * H], want_filters=True)
+        batched_s = time.perf_counter() - tb0
+        d2h = (per_out + 2 * H + per_w) * 8
+        extras["e2e_per_call"] = {"value": K / percall_s, "unit": "updates/s", "ms_per_step": 1e3 * percall_s / K,
+                                  "api": "apvast.process_input_buffers (apv_process_block), one synchronous call per hop",
+                                  "h2d_bytes_per_step": 2 * H * 8, "d2h_bytes_per_step": (per_out + 2 * H) * 8}
+        extras["e2e_batched"] = {"value": K / batched_s, "unit": "updates/s", "ms_per_step": 1e3 * batched_s / K,
+                                 "api": "apvast.process_blocks (apv_process_blocks): K hops in one call, pipelined, "
+                                        "asynchronous D2H ring", "h2d_bytes_per_step": 2 * H * 8, "d2h_bytes_per_step": d2h}
+
+    hbm_peak, peak_src = _peaks()
+    tf = C.c_double(0)
+    capi.check(lib.apv_bench_dmma_peak(4000, C.byref(tf)))
+    dmma_peak = float(tf.value)
+    M_, P_, Nb, F = sh["M"], sh["N"] - sh["J"], sh["Nb"], sh["Nb"] // 2 + 1
+    syrk_flops = 4.0 * M_ * P_ * n * (n + 1)            # SURVEY 8d: SYRK lower triangle, mul+add, 4 matrices
+    ach_tf = syrk_flops / (kt_syrk * 1e-3) / 1e12 if kt_syrk > 0 else 0.0
+    ach_tf_pipe = syrk_flops / (float(kt_pipe[1]) * 1e-3) / 1e12 if kt_pipe[1] > 0 else 0.0
+    ups = world * K / (dev_ms_max * 1e-3)
+    e2e = world * K / (e2e_ms_max * 1e-3)
+    prof = _ncu_profile() or {}
+    seq_ms = float(stage_seq["total"])
+    rl_stats = {"kernel": "syrk_toeplitz_kernel (FP64 DMMA statistics, implicit Toeplitz operand)", "bound": "tensor",
+                "achieved": ach_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach_tf / dmma_peak if dmma_peak else None,
+                "peak_source": "FP64 mma.sync m8n8k4 issue-rate microbenchmark run in this process "
+                               "(MEASURED_PEAKS.json holds HBM and bf16 only)",
+                "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
+                "measured_in": f"sequential section ({Kr} blocks, one stream): CUDA events around the SYRK launches",
+                "share_of_step": kt_syrk / seq_ms if seq_ms > 0 else None,
+                "in_pipelined_region": {"kernel_ms_per_block": float(kt_pipe[1]), "achieved": ach_tf_pipe,
+                                        "note": "shares the SMs with S5-S7 of the previous block"},
+                "traffic": prof.get("dram_bytes_per_block"), "traffic_source": prof.get("source"),
+                "ncu_tensor_pipe_pct": prof.get("tensor_pipe_pct")}
+    two_stage = n_panel < 0
+    others = {}
+    if two_stage:
+        td_flops = 2.0 * 4.0 * n ** 3 / 3.0           # SURVEY 8d: 4 n^3 / 3 per zone
+        td_ms = float(stage_seq.get("S5_tridiag", 0.0))
+        others["roofline_tridiag"] = {
+            "kernel": "two-stage tridiagonalisation (band.cu: sb_panel_qr + DMMA gemm | sb2st_chase)", "bound": "tensor",
+            "achieved": td_flops / (td_ms * 1e-3) / 1e12 if td_ms > 0 else 0.0, "peak": dmma_peak, "unit": "TFLOP/s",
+            "frac": td_flops / (td_ms * 1e-3) / 1e12 / dmma_peak if td_ms > 0 and dmma_peak else None,
+            "algorithmic_flops_per_block": td_flops, "ms_per_block": td_ms, "dense_to_band_ms": kt_panel,
+            "band_to_tridiagonal_ms": float(kt[3]),
+            "note": "latency-bound stages (cluster QR columns, bulge-chasing steps) beside the DMMA GEMMs"}
+        roof = rl_stats
+    else:
         jj = np.arange(n - 1, dtype=np.float64)
-        td_bytes = float(np.sum((n - jj - 1) ** 2) * 8.0 * nz)
+        td_bytes = float(np.sum((n - jj - 1) ** 2) * 8.0 * 2)
         ach = td_bytes / (kt_panel * 1e-3) / 1e9 if kt_panel > 0 else 0.0
-        tf = C.c_double(0)
-        capi.check(lib.apv_bench_dmma_peak(4000, C.byref(tf)))
-        M_, P_ = sh["M"], sh["N"] - sh["J"]
-        syrk_flops = 4.0 * M_ * P_ * n * (n + 1)            # SYRK lower triangle, mul+add, 4 matrices
-        ach_tf = syrk_flops / (kt_syrk * 1e-3) / 1e12 if kt_syrk > 0 else 0.0
-        ups = world * K / (dev_ms_max * 1e-3)
-        e2e = world * K / (e2e_ms_max * 1e-3)
-        two_stage = n_panel < 0
-        rl_stats = {"kernel": "syrk_toeplitz_kernel (FP64 DMMA statistics, implicit Toeplitz operand)", "bound": "tensor",
-                    "achieved": ach_tf, "peak": float(tf.value), "unit": "TFLOP/s",
-                    "frac": ach_tf / float(tf.value) if tf.value else None,
-                    "peak_source": "FP64 mma.sync m8n8k4 issue-rate microbenchmark run in this process "
-                                   "(MEASURED_PEAKS.json holds HBM and bf16 only)",
-                    "algorithmic_flops_per_block": syrk_flops, "kernel_ms_per_block": kt_syrk,
-                    "share_of_step": kt_syrk / (dev_ms_max / K) if dev_ms_max > 0 else None,
-                    "traffic": 1.029e9 * 4,
-                    "traffic_source": "profiles/r01_ncu_full_v3.txt (ncu --set full, one of the 4 launches per block: "
-                                      "7.7 MB read + 1.02 GB written -- the per-microphone partial matrices)",
-                    "ncu_tensor_pipe_pct": 94.4}
-        if two_stage:
-            td_flops = 2.0 * 4.0 * n ** 3 / 3.0           # 4 n^3 / 3 per zone
-            td_ms = float(stage_acc.get("S5_tridiag", 0.0))
-            rl_td = {"kernel": "two-stage tridiagonalisation (band.cu: sb_panel_qr + DMMA gemm | sb2st_chase)",
-                     "bound": "tensor", "achieved": td_flops / (td_ms * 1e-3) / 1e12 if td_ms > 0 else 0.0,
-                     "peak": float(tf.value), "unit": "TFLOP/s",
-                     "frac": td_flops / (td_ms * 1e-3) / 1e12 / float(tf.value) if td_ms > 0 and tf.value else None,
-                     "algorithmic_flops_per_block": td_flops, "ms_per_block": td_ms,
-                     "dense_to_band_ms": kt_panel, "band_to_tridiagonal_ms": float(kt[3]),
-                     "note": "latency-bound stages (cluster QR columns, bulge-chasing steps) beside the DMMA GEMMs"}
-            roof, roof_other = rl_stats, {"roofline_tridiag": rl_td}
+        rl_td = {"kernel": "td_panel_kernel (Householder tridiagonalisation, both zones)", "bound": "hbm",
+                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src,
+                 "algorithmic_bytes_per_block": td_bytes, "launches_per_block": n_panel,
+                 "kernel_ms_per_block": kt_panel, "traffic": None}
+        if kt_panel > kt_syrk:
+            roof, others["roofline_stats"] = rl_td, rl_stats
         else:
-            rl_td = {"kernel": "td_panel_kernel (Householder tridiagonalisation, both zones)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "peak_source": peak_src, "algorithmic_bytes_per_block": td_bytes,
-                     "launches_per_block": n_panel, "kernel_ms_per_block": kt_panel, "traffic": None,
-                     "traffic_sample": {"source": "profiles/r01_ncu_full_v2.txt (ncu --set full, panel 5 of 128, cfg3)",
-                                        "dram_bytes": 8.165e9, "algorithmic_bytes": 7.874e9, "ratio": 1.04}}
-            roof, roof_other = (rl_td, {"roofline_stats": rl_stats}) if kt_panel > kt_syrk else (rl_stats, {"roofline_tridiag": rl_td})
-        line = {
-            "metric": "filter_updates_per_sec", "value": ups, "unit": "updates/s", "rtf": ups * H / FS,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: synthetic 2-zone L={sh['L']} M={sh['M']} J={sh['J']} n={n} "
-                                   f"K={sh['K']} Nb={sh['Nb']} H={H} N={sh['N']} V={V} fs=48000",
-                       "sharding": f"contiguous block ranges over {world} rank(s), no per-block collective",
-                       "l2": "per-block working set ~1.6 GB (4 R + jdiag workspace) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e, "unit": "updates/s", "rtf": e2e * H / FS, "ms_per_step": e2e_ms_max / K,
-                    "h2d_bytes_per_step": 2 * H * 8, "d2h_bytes_per_step": (2 * V * H * L + 2 * H) * 8 + 32},
-            "gpu_launches": launches,
-            "roofline": roof,
-            "stage_ms_last_block": stage_acc, "clocks": clocks, "checksum": chk,
-        }
-        line.update(roof_other)
-        line["alt_structured_stats"] = alt
-        if world == 1 and not args.no_cpu_baseline:
-            wl = make_workload(args.workload, n_blocks=8)
-            times, split, sample = cpu_reference_sample(wl, 1, 3)
-            line["cpu_baseline"] = {"value": 1.0 / float(np.mean(times)), "unit": "updates/s", "cores": blas_threads(),
-                                    "kind": "port", "sample": sample, "split_s": split, "host_cpus": os.cpu_count()}
-        print(json.dumps(line), flush=True)
-    eng.close()
+            roof, others["roofline_tridiag"] = rl_stats, rl_td
+
+    def hbm_line(kernel, ms_, bytes_, formula):
+        a = bytes_ / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": kernel, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_block": bytes_, "formula": formula, "ms_per_block": ms_,
+                "measured_in": "sequential section, CUDA events at the stage boundaries"}
+
+    others["roofline_render"] = hbm_line("render_kernel + render_target_kernel (S7)", stage_seq["S7_render"],
+                                         (2 * V + 2) * L * (3 * H * 8 + F * 16), "(2V+2) L (3H 8 + F 16)  [SURVEY 8d]")
+    others["roofline_wola"] = hbm_line("wola_target_kernel + wola_resp_kernel (S2, S3)", stage_seq["S2S3_wola_weight"],
+                                       (4 * L * M_ + 2 * M_) * 8 * (2 * Nb + 2 * H + sh["N"]),
+                                       "(4LM+2M) 8 (2Nb + 2H + N)  [SURVEY 8d]")
+    others["roofline_sweep"] = hbm_line("sweep_dot_kernel + sweep_prefix_kernel (S6)", stage_seq["S6_sweep"],
+                                        2 * (2 * V * n * 8 + V * n * 8), "2 zones (read U twice, write w): 3 V n 8")
+
+    line = {
+        "metric": "filter_updates_per_sec", "value": ups, "unit": "updates/s", "rtf": ups * H / FS,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sh, world),
+        "e2e": {"value": e2e, "unit": "updates/s", "rtf": e2e * H / FS, "ms_per_step": e2e_ms_max / K,
+                "h2d_bytes_per_step": 2 * H * 8 * ((rr.halo + K) / K if world > 1 else 1),
+                "d2h_bytes_per_step": (per_out + per_w) * 8,
+                "api": "apv_range_run + apv_range_exchange_halo + apv_range_gather (sharded.RangeRunner), host buffers"},
+        "gpu_launches": launches_block * K + 4 * n_halo + 3,
+        "timed_region": {"per_rank": f"{rr.halo} halo blocks (S1-S3; rank 0 has none) + {K} owned blocks "
+                                     f"(pipelined: S1-S4 of block t+1 overlap S5-S7 of block t) + overlap-add tail "
+                                     f"exchange + gather to rank 0",
+                         "pipeline": not args.no_pipeline, "launches_per_block": launches_block},
+        "collective": {"halo": {"op": "ncclSend/ncclRecv (device to device, issued by the library on the engine's stream)",
+                                "messages": world - 1, "bytes_per_message": rr.bytes_halo},
+                       "gather": {"op": "ncclSend/ncclRecv to rank 0", "bytes": (world - 1) * K * (per_out + per_w) * 8,
+                                  "d2h_on_rank0_bytes_e2e": world * K * (per_out + per_w) * 8}},
+        "boundary_check": boundary,
+        "roofline": roof,
+        "stage_ms_sequential_block": stage_seq, "stage_ms_pipelined_last_block": stage_pipe,
+        "clocks": clocks, "checksum": chk,
+    }
+    line.update(others)
+    line.update(extras)
+
+    # ---- alternative configuration (not the headline): statistics by the structured evaluation (stats_mode=2)
+    if world == 1 and not args.no_alt:
+        rr.close(); eng.close()
+        np.random.seed(0)
+        eng2 = apvast(rir_A=full["rir_A"], rir_B=full["rir_B"], perceptual=False, device=local_rank, stats_mode=2,
+                      **full["cfg"])
+        if args.no_pipeline:
+            eng2.set_pipeline(False)
+        r2 = RangeRunner(eng2, 0, 1, None, max_owned=max(K, W), total_blocks=max(K, W))
+        s2 = eng2.get_state()
+        r2.run(None, None, 0, Wb, device_ptrs=(ptrA, ptrB)); r2.gather([Wb], None, None)
+        eng2.set_state(s2)
+        torch.cuda.synchronize()
+        capi.check(lib.apv_timer_start(eng2._h))
+        r2.run(None, None, 0, K, device_ptrs=(ptrA, ptrB)); r2.gather([K], None, None)
+        ms2 = C.c_float(0)
+        capi.check(lib.apv_timer_stop(eng2._h, C.byref(ms2)))
+        capi.check(lib.apv_process_block_device(eng2._h, C.c_void_p(ptrA), C.c_void_p(ptrB)))
+        st2 = eng2.stage_times()
+        line["alt_structured_stats"] = {
+            "what": "same workload with stats_mode=2 (first-row correlations + double-double diagonal recurrence "
+                    "instead of the DMMA SYRK; identical parity, ~J/2 x fewer flops); device-timed like `value`",
+            "value": K / (float(ms2.value) * 1e-3), "unit": "updates/s", "ms_per_step": float(ms2.value) / K,
+            "S4_stats_ms_sequential": st2["S4_stats"]}
+        r2.close(); eng2.close()
+    else:
+        rr.close(); eng.close()
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args.workload)
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -411,16 +575,25 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "small"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "small", "cfg4", "cfg5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra measurement of the structured-statistics mode")
+    ap.add_argument("--no-pipeline", action="store_true", help="blocks strictly one after the other (diagnostic)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in ("cfg4", "cfg5"):
+        from scripts import bench_extra
+        if world == 1 and args.gpus > 1 and args.workload == "cfg5":
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        bench_extra.run(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return

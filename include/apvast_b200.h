@@ -148,6 +148,9 @@ int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B);
 /* 0: consecutive blocks of a multi-block call strictly in order on one stream; 1 (default, also env APV_PIPELINE):
  * S1-S4 of block t+1 overlap S5-S7 of block t.  Results are bit-identical either way. */
 int apv_set_pipeline(apv_handle* h, int on);
+/* Diagnostic timeline of a multi-block call: arm with ms == NULL, run, read back (nblocks, 4) milliseconds
+ * (front start, front end, back start, back end per block, relative to the first event). */
+int apv_debug_timeline(apv_handle* h, int nblocks, float* ms);
 /* EXPERIMENTAL_REGULARIZATION (apvast.py:7,22-27), read by the reference at call time: 0 = absolute reg (default),
  * 1 = 1e-8 |R_D|_2 (spectral norm by power iteration on the device). */
 int apv_set_reg_mode(apv_handle* h, int relative);

@@ -12,7 +12,9 @@ from .apvast_oracle import ApvastOracle, jdiag
 
 class MultiZoneOracle:
     def __init__(self, block_size, rirs, filter_length, modeling_delay, reference_indices, number_of_eigenvectors, mu,
-                 statistics_buffer_length, hop_size=None, seed=0):
+                 statistics_buffer_length, hop_size=None, seed=0, perceptual=False):
+        # perceptual=True: the pair oracle (z, q) weights zone-z microphones from target z and zone-q microphones from
+        # target q (apvast.py:259-262,318-319) -- every microphone is weighted from its own zone's target
         self.Z = len(rirs)
         self.V, self.mu = int(number_of_eigenvectors), float(mu)
         self.pairs = {}
@@ -23,7 +25,7 @@ class MultiZoneOracle:
                 np.random.seed(seed)
                 self.pairs[(z, q)] = ApvastOracle(block_size, rirs[z], rirs[q], filter_length, modeling_delay,
                                                   reference_indices[z], reference_indices[q], 1, mu,
-                                                  statistics_buffer_length, hop_size, perceptual=False)
+                                                  statistics_buffer_length, hop_size, perceptual=perceptual)
 
     def process_input_buffers(self, inputs):
         for (z, q), o in self.pairs.items():

@@ -221,51 +221,90 @@ def test_process_blocks_and_checkpoint_roundtrip(tmp_path):
         assert np.array_equal(o, outs1[t]), t
 
 
-@pytest.mark.parametrize("stats_mode", [0, 2])
-def test_cfg3_against_reference_golden(stats_mode):
-    """BASELINE cfg-3 (L=16, J=256, n=4096): 5 hops against what the UNMODIFIED reference produced on the same
-    synthetic workload (tests/golden/cfg3_reference.npz, oracle/make_golden_cfg3.py, ~1 min of CPU per hop)."""
+def _golden_run(fname, workload, stats_mode, bars):
+    """Replay a size-named golden file (oracle/make_golden_cfg3.py: the UNMODIFIED reference on the deterministic
+    synthetic workload) and return (worst errors, violations)."""
     import os
     from ap_vast_unofficial_b200.workloads import make_workload
     from tests._golden import GOLDEN
-    z = np.load(os.path.join(GOLDEN, "cfg3_reference.npz"))
-    nblk = int(z["nblk"]); ranks = list(z["ranks"])
-    wl = make_workload("cfg3", n_blocks=nblk)
+    z = np.load(os.path.join(GOLDEN, fname))
+    nblk = int(z["nblk"]); sub = list(z["ranks"])
+    variant = int(z["variant"]) if "variant" in z.files else 0
+    all_from = int(z["all_ranks_from"]) if "all_ranks_from" in z.files else -1
+    wl = make_workload(workload, n_blocks=nblk, variant=variant)
     np.random.seed(int(z["seed"]))
     eng = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, stats_mode=stats_mode, **wl["cfg"])
     H, V = eng.hop_size, eng.number_of_eigenvectors
     n = eng.filter_length * eng.number_of_srcs
-    worst = {}
-    fails = []
+    worst, fails = {}, []
     for t in range(nblk):
         outs = eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+        ranks = list(range(V)) if 0 <= all_from <= t else sub
         for nm in ("R_A_to_A", "R_A_to_B", "R_B_to_A", "R_B_to_B"):
             R = getattr(eng, nm)
             e = max(rel(np.diag(R), z[f"{nm}_diag_{t}"]), rel(R[[0, n // 2 - 1, n - 1], :], z[f"{nm}_rows_{t}"]))
             worst["R"] = max(worst.get("R", 0), e)
-            assert e < 1e-12, (t, nm, e)
+            if e >= bars["R"]:
+                fails.append((t, nm, e))
         for zn in ("A", "B"):
-            assert rel(getattr(eng, f"r_{zn}")[:, 0], z[f"r_{zn}_{t}"]) < 1e-12
+            e = rel(getattr(eng, f"r_{zn}")[:, 0], z[f"r_{zn}_{t}"])
+            if e >= bars["R"]:
+                fails.append((t, "r_" + zn, e))
             lam_ref = z[f"lambda_{zn}_{t}"]
             lam = getattr(eng, f"lambda_{zn}")
             el = float(np.max(np.abs(lam - lam_ref[:V])) / lam_ref[0])
             worst["lambda"] = max(worst.get("lambda", 0), el)
-            assert el < 1e-9, (t, zn, el)       # eps * cond(R_D + reg I): the pencil is ill-conditioned at this size
+            if el >= bars["lambda"]:
+                fails.append((t, "lambda_" + zn, el))
             gap = np.abs(np.diff(lam_ref)) / lam_ref[0]          # V gaps (V+1 eigenvalues stored)
             w = getattr(eng, f"w_{zn}")[:, :, 0]
             for i, v in enumerate(ranks):
                 e = rel(w[v], z[f"w_{zn}_{t}"][i])
-                key = "w_resolved" if gap[v] > 1e-6 else "w_close_pair"
-                worst[key] = max(worst.get(key, 0), e)
-                # 1e-8 is the north-star bar; it is reachable only where the reference's own filter is well
-                # defined, i.e. the eigenvalue gap to the next rank is resolved (SURVEY 7.3)
-                fails.append((t, zn, v, e, float(gap[v]))) if e >= (1e-8 if gap[v] > 1e-6 else 1e-5) else None
+                # a rank whose eigenvalue gap to the next one is not resolved (relative gap <= 1e-9) has no well-defined
+                # filter in the reference either (SURVEY 7.3); everything else is held to the north-star bar
+                if gap[v] > 1e-9:
+                    worst["w"] = max(worst.get("w", 0), e)
+                    if e >= bars["w"]:
+                        fails.append((t, zn, v, e, float(gap[v])))
+                else:
+                    worst["w_unresolved"] = max(worst.get("w_unresolved", 0), e)
         for i, zn in enumerate(("A", "B")):
             got = np.stack([outs[i][v] for v in (0, V - 1)])
             e = rel(got, z[f"out_{zn}_{t}"])
             worst["out"] = max(worst.get("out", 0), e)
-            fails.append((t, "out_" + zn, e)) if e >= 1e-7 else None
+            if e >= bars["out"]:
+                fails.append((t, "out_" + zn, e))
+    eng.close()
+    return worst, fails
+
+
+# bars = the claims of DESIGN.md section 2: statistics 1e-12, eigenvalues 1e-10, filters 1e-8 (north star), outputs 1e-9
+_BARS = dict(R=1e-12, **{"lambda": 1e-10}, w=1e-8, out=1e-9)
+
+
+@pytest.mark.parametrize("stats_mode", [0, 2])
+def test_cfg3_against_reference_golden(stats_mode):
+    """BASELINE cfg-3 (L=16, J=256, n=4096): 5 hops against what the UNMODIFIED reference produced on the same
+    synthetic workload (tests/golden/cfg3_reference.npz, oracle/make_golden_cfg3.py, ~1 min of CPU per hop)."""
+    worst, fails = _golden_run("cfg3_reference.npz", "cfg3", stats_mode, _BARS)
     print("cfg3 vs reference golden (stats_mode=%d): worst relative errors" % stats_mode, worst, "violations", fails)
+    assert not fails, fails
+
+
+def test_cfg3_second_golden_all_ranks_past_warmup():
+    """A second draw of the cfg-3 workload (other RIRs, other programme signals), 8 hops so that four of them are
+    fully signal-driven, ALL 64 ranks of those four hops (tests/golden/cfg3_reference_v1.npz)."""
+    worst, fails = _golden_run("cfg3_reference_v1.npz", "cfg3", 0, _BARS)
+    print("cfg3 (variant 1) vs reference golden: worst relative errors", worst, "violations", fails)
+    assert not fails, fails
+
+
+@pytest.mark.parametrize("stats_mode", [0, 2])
+def test_cfg2_against_reference_golden(stats_mode):
+    """BASELINE cfg-2 (L=8, J=128, n=1024): 10 hops, all 64 ranks, against the unmodified reference
+    (tests/golden/cfg2_reference.npz)."""
+    worst, fails = _golden_run("cfg2_reference.npz", "cfg2", stats_mode, _BARS)
+    print("cfg2 vs reference golden (stats_mode=%d): worst relative errors" % stats_mode, worst, "violations", fails)
     assert not fails, fails
 
 

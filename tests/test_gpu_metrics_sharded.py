@@ -42,6 +42,43 @@ def test_contrast_and_distortion_within_001_db():
             assert abs(nsd_g - nsd_o) < 0.01, (v, z, nsd_g, nsd_o)
 
 
+def test_cfg1_contrast_and_distortion_against_reference_feeds():
+    """North-star criterion on the reference's own fixture: the make_python_test.m case on Python/rirs.mat, 16 hops.
+    AC / NSD of the GPU engine's feeds at the control microphones of rirs.mat within 0.01 dB of the AC / NSD of the feeds
+    the UNMODIFIED reference rendered (tests/golden/cfg1_feeds.npz, oracle/make_golden_cfg1_feeds.py), evaluated both on
+    the device (apv_eval_zone) and with the host definitions."""
+    import os
+    from ap_vast_unofficial_b200 import apvast
+    from ap_vast_unofficial_b200.metrics import evaluate_zone
+    from tests._golden import GOLDEN, load_case
+    g1, _, _ = load_case("cfg1")
+    z = np.load(os.path.join(GOLDEN, "cfg1_feeds.npz"))
+    cfg = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg_")}
+    rA, rB = g1["rir_A"], g1["rir_B"]
+    nblk, skip, ranks = int(z["nblk"]), int(z["skip"]), list(z["ranks"])
+    np.random.seed(int(z["seed"]))
+    eng = apvast(rir_A=rA, rir_B=rB, perceptual=False, **cfg)
+    H = eng.hop_size
+    sA, sB = z["input_A"], z["input_B"]
+    fa, fb = [], []
+    for t in range(nblk):
+        oA, oB, _, _ = eng.process_input_buffers(sA[t * H:(t + 1) * H], sB[t * H:(t + 1) * H])
+        fa.append(np.stack([oA[v] for v in ranks])); fb.append(np.stack([oB[v] for v in ranks]))
+    fa, fb = np.concatenate(fa, axis=1), np.concatenate(fb, axis=1)
+    worst = 0.0
+    for i in range(len(ranks)):
+        assert rel(fa[i], z["feeds_A"][i]) < 1e-8 and rel(fb[i], z["feeds_B"][i]) < 1e-8
+        for zi, (f, rb, rd, sig, zone) in enumerate(((fa[i], rA, rB, sA, "A"), (fb[i], rB, rA, sB, "B"))):
+            ac_ref, nsd_ref = z["metrics"][i, zi]
+            ac_h, nsd_h = evaluate_zone(f[skip * H:], rb, rd, sig[skip * H:], cfg["reference_index_A"], cfg["modeling_delay"])
+            ac_d, _, nsd_d = eng.evaluate(f[skip * H:], sig[skip * H:], zone)
+            worst = max(worst, abs(ac_h - ac_ref), abs(nsd_h - nsd_ref), abs(ac_d - ac_ref), abs(nsd_d - nsd_ref))
+            assert abs(ac_h - ac_ref) < 0.01 and abs(nsd_h - nsd_ref) < 0.01, (i, zone, ac_h, ac_ref, nsd_h, nsd_ref)
+            assert abs(ac_d - ac_ref) < 0.01 and abs(nsd_d - nsd_ref) < 0.01, (i, zone, ac_d, ac_ref, nsd_d, nsd_ref)
+    print("cfg-1 AC/NSD vs reference feeds: worst |delta| = %.2e dB" % worst)
+    eng.close()
+
+
 def test_device_metrics_match_host_definitions():
     """apv_eval_zone (pressure + energies on the device) against the NumPy definitions of metrics.py."""
     from ap_vast_unofficial_b200 import apvast
@@ -96,8 +133,8 @@ def test_sharded_two_ranks_emulated_matches_single_stream():
     rA, rB, cfg, sA, sB, nblk = _case(nblk=16, seed=33)
     make = lambda: apvast(rir_A=rA, rir_B=rB, **cfg)
     ref = process_signal_sharded(make, sA, sB, seed=0)
-    r0 = process_signal_sharded(make, sA, sB, rank=0, world=2, dist=_FakeDist(0), seed=0)
-    r1 = process_signal_sharded(make, sA, sB, rank=1, world=2, dist=_FakeDist(1), seed=0)
+    r0 = process_signal_sharded(make, sA, sB, rank=0, world=2, dist=_FakeDist(0), seed=0, gather=False)
+    r1 = process_signal_sharded(make, sA, sB, rank=1, world=2, dist=_FakeDist(1), seed=0, gather=False)
     assert r0["blocks"] == (0, 8) and r1["blocks"] == (8, 16)
     outs = r0["out_A"] + r1["out_A"]
     ws = r0["w_A"] + r1["w_A"]
