@@ -72,6 +72,7 @@ SIGNATURES = {
     "apv_set_mu": (C.c_int, [C.c_void_p, C.c_double]),
     "apv_set_gain_table": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, C.c_double]),
     "apv_sweep": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "apv_sweep_device": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_void_p, _dp]),
     "apv_eval_zone": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
     "apv_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "apv_synchronize": (C.c_int, [C.c_void_p]),

@@ -303,6 +303,16 @@ class apvast:
         capi.check(capi.lib().apv_sweep(self._h, mus.size, capi.ptr(mus), capi.ptr(out)))
         return (out[:, 0] if self.run_A else None), (out[:, 1] if self.run_B else None)
 
+    def sweep_metrics(self, mu_values, device_out=None):
+        """Eigen-basis figures of merit of the mu x V sweep, (n_mu, 2, V, 3): dark energy ``w'(R_D + reg I)w``, bright
+        energy ``w'R_B w`` and ``w'r_B`` of every rank's filter, from the joint diagonalisation of the last block.
+        ``device_out``: optional device pointer of an (n_mu, 2, V, n) buffer that receives the filters themselves."""
+        mus = np.ascontiguousarray(mu_values, dtype=np.float64).reshape(-1)
+        out = np.zeros((mus.size, 2, self.number_of_eigenvectors, 3))
+        capi.check(capi.lib().apv_sweep_device(self._h, mus.size, capi.ptr(mus),
+                                               None if device_out is None else C.c_void_p(device_out), capi.ptr(out)))
+        return out
+
     def evaluate(self, feeds, signal, zone="A"):
         """Acoustic contrast and normalised signal distortion of loudspeaker feeds (T, L) at the control microphones,
         on the device (``predictPressure.m:12-17``, ``main.m:120-130``).  Returns (AC dB, NMSE, NSD dB)."""

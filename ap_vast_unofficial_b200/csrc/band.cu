@@ -1295,4 +1295,132 @@ int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches) {
   return OK;
 }
 
+// Aggregation of the compact-WY factors of `gs` consecutive panels (gs <= 4) into ONE block reflector of width 32 gs:
+//   H_1 ... H_gs = I - V T V^T,  V = [V_1 ... V_gs],  T upper triangular with the panels' own T_j on the diagonal and
+//   T[0:32j, j] = -T[0:32j, 0:32j] (V_{1..j}^T V_j) T_j   (the dlarft recurrence on blocks).
+// G = V^T V arrives as `nsplit` K-slice partials of a split GEMM.   grid (nz), 256 threads.
+__global__ void __launch_bounds__(256) q1_aggregate_kernel(const double* __restrict__ Gpart, int nsplit, int split_cap,
+                                                           const double* __restrict__ Tpan, int nz, int gs,
+                                                           double* __restrict__ Tg, long long tg_stride) {
+  extern __shared__ double agsm[];
+  const int z = blockIdx.x, W = NB2 * gs, tid = threadIdx.x;
+  double* G = agsm;                 // [W][W]   Gram matrix (sum of the K-slice partials)
+  double* tmp = G + W * W;          // [W][32]
+  double* T = Tg + (size_t)z * tg_stride;      // [W][128] in global memory (64 KB, L1/L2 resident)
+  const double* gp = Gpart + (size_t)z * split_cap * 128 * 128;     // (the zone stride of the split GEMM's output)
+  for (int e = tid; e < W * W; e += 256) {
+    const int i = e / W, j = e % W;
+    double acc = 0.0;
+    for (int q = 0; q < nsplit; ++q) acc += gp[(size_t)q * 128 * 128 + i * 128 + j];
+    G[e] = acc;
+    T[i * 128 + j] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < gs; ++j) {          // the panels' own factors on the diagonal
+    const double* tp = Tpan + ((size_t)j * nz + z) * NB2 * NB2;
+    for (int e = tid; e < NB2 * NB2; e += 256) T[(j * NB2 + e / NB2) * 128 + j * NB2 + e % NB2] = tp[e];
+  }
+  __syncthreads();
+  for (int j = 1; j < gs; ++j) {
+    const int R = NB2 * j;               // rows above the diagonal block of block column j
+    // tmp = G[0:R, j] T_j
+    for (int e = tid; e < R * NB2; e += 256) {
+      const int i = e / NB2, c = e % NB2;
+      double acc = 0.0;
+      for (int k = 0; k < NB2; ++k) acc = fma(G[i * W + j * NB2 + k], T[(j * NB2 + k) * 128 + j * NB2 + c], acc);
+      tmp[e] = acc;
+    }
+    __syncthreads();
+    // T[0:R, j] = -T[0:R, 0:R] tmp
+    for (int e = tid; e < R * NB2; e += 256) {
+      const int i = e / NB2, c = e % NB2;
+      double acc = 0.0;
+      for (int k = i; k < R; ++k) acc = fma(T[i * 128 + k], tmp[k * NB2 + c], acc);      // (T is upper triangular)
+      T[i * 128 + j * NB2 + c] = -acc;
+    }
+    __syncthreads();
+  }
+}
+
+// The same back-transformation for MANY vectors (full-spectrum requests, V > n / 8: BASELINE cfg-4), as tensor-core
+// GEMMs on the n x Vp matrix of vectors X (slot 4 of the inverse-iteration workspace, row-major).  Four consecutive
+// panels are aggregated into one block reflector of width 128 (q1_aggregate_kernel), so that every product has a
+// full 128-row tile; per group, last to first:  S = V_g^T X[r:, :]  (128 x Vp, K = n - r),  U = T_g S,
+// X[r:, :] -= V_g U  (rank-128 update).  The slab kernel above streams the reflectors once per chunk of 64 vectors (64
+// launches of ~3 ms at V = n = 4096); here they are streamed once and the O(n^2 V) work runs on the DMMA pipe.
+// X is transformed in place; the caller moves it on.
+int twostage_apply_q1_gemm(JdiagWs& ws, cudaStream_t st, int* launches) {
+  const int n = ws.n, nz = ws.nz, ldn = ws.ldn, Vp = ws.Vp;
+  constexpr int GS = 4, GW = GS * NB2, NSPLIT = 16;
+  int npanels = 0;
+  for (int j0 = 0; n - j0 - NB2 >= 2; j0 += NB2) ++npanels;
+  if (npanels == 0) return OK;
+  const int ngroups = ceil_div(npanels, GS);
+  const double* Tall = ws.ts2 + (size_t)nz * n * NB2 * (2 + twostage_nsplit_max()) + (size_t)nz * ceil_div(n, 64) * NB2 * NB2;
+  const size_t need = (size_t)nz * ngroups * GW * GW + (size_t)nz * NSPLIT * GW * GW + 2 * (size_t)nz * GW * Vp;
+  if (ws.q1agg_count < need) {
+    if (ws.q1agg) cudaFree(ws.q1agg);
+    ws.q1agg = nullptr; ws.q1agg_count = 0;
+    APV_CUDA_TRY(cudaMalloc((void**)&ws.q1agg, need * sizeof(double)));
+    ws.q1agg_count = need;
+  }
+  double* Tg = ws.q1agg;                                        // [nz][ngroups][128][128]
+  double* Gpart = Tg + (size_t)nz * ngroups * GW * GW;          // [nz][NSPLIT][128][128]
+  double* S = Gpart + (size_t)nz * NSPLIT * GW * GW;            // [nz][128][Vp]
+  double* U = S + (size_t)nz * GW * Vp;
+  const long long tgs = (long long)ngroups * GW * GW, ss = (long long)GW * Vp;
+  double* X = ws.iv + 4 * (size_t)n * Vp;
+  const long long xs = 6LL * n * Vp;             // zone stride of the workspace
+  const size_t agsm = (size_t)(GW * GW + GW * NB2) * sizeof(double);
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
+  if (!configured) {
+    APV_CUDA_TRY(cudaFuncSetAttribute(q1_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agsm));
+    configured = 1;
+  }
+  // ---- the aggregated T factors
+  for (int g = 0; g < ngroups; ++g) {
+    const int p0 = g * GS, gs = std::min(GS, npanels - p0), j0 = p0 * NB2, r = j0 + NB2, rows = n - r, Mg = NB2 * gs;
+    const int kslice = round_up(ceil_div(rows, NSPLIT), 16);
+    const int nsplit = ceil_div(rows, kslice);
+    GemmArgs gr{};
+    gr.batch = nz; gr.split = nsplit; gr.split_ktot = rows;
+    gr.A = ws.VH + (size_t)j0 * ldn + r; gr.lda = ldn; gr.strideA = (long long)n * ldn; gr.splitA = kslice;
+    gr.B = gr.A; gr.ldb = ldn; gr.strideB = gr.strideA; gr.splitB = kslice; gr.transB = 1;
+    gr.C = Gpart; gr.ldc = GW; gr.strideC = (long long)NSPLIT * GW * GW; gr.splitC = (long long)GW * GW;
+    gr.M = Mg; gr.N = Mg; gr.K = kslice; gr.alpha = 1.0; gr.beta = 0.0;
+    APV_TRY(gemm_f64(gr, st));
+    q1_aggregate_kernel<<<nz, 256, agsm, st>>>(Gpart, nsplit, NSPLIT, Tall + (size_t)p0 * nz * NB2 * NB2, nz, gs,
+                                               Tg + (size_t)g * GW * GW, tgs);
+    *launches += 2;
+  }
+  // ---- apply the block reflectors, last group first
+  for (int g = ngroups - 1; g >= 0; --g) {
+    const int p0 = g * GS, gs = std::min(GS, npanels - p0), j0 = p0 * NB2, r = j0 + NB2, rows = n - r, Mg = NB2 * gs;
+    GemmArgs a{};
+    a.batch = nz;
+    a.A = ws.VH + (size_t)j0 * ldn + r; a.lda = ldn; a.strideA = (long long)n * ldn;      // V_g^T: Mg x rows
+    a.B = X + (size_t)r * Vp; a.ldb = Vp; a.strideB = xs;
+    a.C = S; a.ldc = Vp; a.strideC = ss;
+    a.M = Mg; a.N = Vp; a.K = rows; a.alpha = 1.0; a.beta = 0.0; a.bn = 64;
+    APV_TRY(gemm_f64(a, st));
+    GemmArgs t{};
+    t.batch = nz;
+    t.A = Tg + (size_t)g * GW * GW; t.lda = GW; t.strideA = tgs;
+    t.B = S; t.ldb = Vp; t.strideB = ss;
+    t.C = U; t.ldc = Vp; t.strideC = ss;
+    t.M = Mg; t.N = Vp; t.K = Mg; t.alpha = 1.0; t.beta = 0.0;
+    APV_TRY(gemm_f64(t, st));
+    GemmArgs u{};
+    u.batch = nz;
+    u.A = a.A; u.lda = ldn; u.strideA = a.strideA; u.transA = 1;                           // V_g: rows x Mg, stored Mg x rows
+    u.B = U; u.ldb = Vp; u.strideB = ss;
+    u.C = X + (size_t)r * Vp; u.ldc = Vp; u.strideC = xs;
+    u.M = rows; u.N = Vp; u.K = Mg; u.alpha = -1.0; u.beta = 1.0;
+    APV_TRY(gemm_f64(u, st));
+    *launches += 3;
+  }
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
 }  // namespace apv

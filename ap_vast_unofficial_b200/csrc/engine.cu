@@ -765,17 +765,54 @@ int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out) {
   DevGuard dg(h->device);
   const Dims& D = h->D;
   const size_t cnt = 2 * (size_t)D.V * D.n;
-  double* tmp = nullptr;
-  APV_CUDA_TRY(cudaMalloc((void**)&tmp, cnt * sizeof(double)));
-  APV_CUDA_TRY(cudaMemsetAsync(tmp, 0, cnt * sizeof(double), h->st));
+  // chunks of mu values so that the device buffer stays below ~1 GB
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_mu, ((size_t)1 << 30) / (cnt * sizeof(double))));
+  double *tmp = nullptr, *d_mu = nullptr;
+  APV_CUDA_TRY(cudaMalloc((void**)&tmp, (size_t)chunk * cnt * sizeof(double)));
+  APV_CUDA_TRY(cudaMalloc((void**)&d_mu, n_mu * sizeof(double)));
   int rc = OK;
-  for (int i = 0; i < n_mu && rc == OK; ++i) {
-    rc = stage_sweep(*h, mu[i], tmp);
-    if (rc == OK && cudaMemcpyAsync(w_out + (size_t)i * cnt, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess)
+  if (cudaMemcpyAsync(d_mu, mu, n_mu * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess) rc = fail(ECUDA, "mu copy failed");
+  for (int i = 0; i < n_mu && rc == OK; i += chunk) {
+    const int c = std::min(chunk, n_mu - i);
+    cudaMemsetAsync(tmp, 0, (size_t)c * cnt * sizeof(double), h->st);
+    rc = stage_sweep_multi(*h, c, d_mu + i, tmp);
+    if (rc == OK && cudaMemcpyAsync(w_out + (size_t)i * cnt, tmp, (size_t)c * cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess)
       rc = fail(ECUDA, "sweep copy failed");
+    cudaStreamSynchronize(h->st);
+  }
+  cudaFree(tmp);
+  cudaFree(d_mu);
+  return rc;
+}
+
+/* Sweep without leaving the device: filters for every mu into a caller-owned DEVICE buffer (n_mu, 2, V, n) (may be
+ * NULL) and the eigen-basis figures of merit (n_mu, 2, V, 3) = {dark energy, bright energy, w . r_B} per rank to the
+ * host (may be NULL).  The full-rank sweep of BASELINE cfg-4 is 2 GB of filters per block: they stay in HBM. */
+int apv_sweep_device(apv_handle* h, int n_mu, const double* mu, void* d_w_out, double* metrics_out) {
+  if (!h || !mu || n_mu < 1) return fail(EINVAL_, "bad argument");
+  DevGuard dg(h->device);
+  const Dims& D = h->D;
+  double *d_mu = nullptr, *d_m = nullptr;
+  const size_t mc = (size_t)n_mu * 2 * D.V * 3;
+  APV_CUDA_TRY(cudaMalloc((void**)&d_mu, n_mu * sizeof(double)));
+  int rc = OK;
+  if (cudaMemcpyAsync(d_mu, mu, n_mu * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess) rc = fail(ECUDA, "mu copy failed");
+  if (rc == OK && d_w_out) {
+    if (!(D.runA && D.runB)) cudaMemsetAsync(d_w_out, 0, (size_t)n_mu * 2 * D.V * D.n * sizeof(double), h->st);
+    rc = stage_sweep_multi(*h, n_mu, d_mu, (double*)d_w_out);
+  }
+  if (rc == OK && metrics_out) {
+    if (cudaMalloc((void**)&d_m, mc * sizeof(double)) != cudaSuccess) rc = fail(ECUDA, "cudaMalloc failed");
+    if (rc == OK) {
+      cudaMemsetAsync(d_m, 0, mc * sizeof(double), h->st);
+      rc = stage_sweep_metrics(*h, n_mu, d_mu, d_m);
+    }
+    if (rc == OK && cudaMemcpyAsync(metrics_out, d_m, mc * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess)
+      rc = fail(ECUDA, "metrics copy failed");
   }
   cudaStreamSynchronize(h->st);
-  cudaFree(tmp);
+  cudaFree(d_mu);
+  if (d_m) cudaFree(d_m);
   return rc;
 }
 

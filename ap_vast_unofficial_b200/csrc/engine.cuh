@@ -39,6 +39,8 @@ struct JdiagWs {
   double* iv = nullptr;     // [nz][6][n][Vp] inverse-iteration work (interleaved over vectors)
   double* Zt = nullptr;     // [nz][V][n] eigenvectors of T -> of C -> joint eigenvectors U (row v)
   int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
+  double* q1agg = nullptr;  // aggregated block reflectors + scratch of the GEMM back-transformation (allocated on first use)
+  size_t q1agg_count = 0;
   double* ts2 = nullptr;    // two-stage tridiagonalisation scratch (band.cu): V panel, Y slices, X, S partials, T, band, flags
   cudaEvent_t ev2[4] = {};  // two-stage: end of stage 1 (dense -> band), end of stage 2 (band -> tridiagonal), look-ahead fork / join
   cudaStream_t st2 = nullptr;   // high-priority side stream of the look-ahead panel factorisation
@@ -63,6 +65,7 @@ int twostage_nsplit_max();
 int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches);   // then by the stage-1 block reflectors -> Zt
+int twostage_apply_q1_gemm(JdiagWs& ws, cudaStream_t st, int* launches);   // many vectors: DMMA GEMMs, in place in iv slot 4
 // regv != nullptr: per-zone diagonal loading read from device memory instead of `reg`.
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
               cudaStream_t st, int* launches, const double* regv = nullptr);
@@ -172,6 +175,8 @@ int stage_weighted(Handle& h);                                                //
 int stage_stats(Handle& h);                                                   // S4 (stats.cu)
 int stage_loading(Handle& h);                                                 // MATLAB diagonal loading (stats.cu)
 int stage_sweep(Handle& h, double mu, double* W_out);                         // S6 (render.cu)
+int stage_sweep_multi(Handle& h, int n_mu, const double* d_mu, double* W_out);     // list of mu, one launch
+int stage_sweep_metrics(Handle& h, int n_mu, const double* d_mu, double* d_out);   // eigen-basis metrics of the sweep
 int stage_render(Handle& h);                                                  // a2 + S7
 int eval_zone(Handle& h, int zone, int T, const double* feeds, const double* signal, double* out3);  // metrics.cu
 int stage_spectral_norms(Handle& h);                                          // |R_D|_2 per zone -> regv (stats.cu)

@@ -309,7 +309,7 @@ int stage_targets(Handle& h, bool only_frame) {
   APV_TRY(ensure_smem(wola_target_kernel, sm));
   wola_target_kernel<<<dim3(D.M, 2), 256, sm, h.st>>>(h.QT, h.OT, h.ST, h.Wg, h.tframe, h.win, h.tw, make_plan(h),
                                                       h.G2, h.nchan, h.Cs, h.Ca, h.Leff, h.cfg.normalize_gains,
-                                                      h.cfg.perceptual, only_frame ? 1 : 0, D);
+                                                      h.cfg.perceptual == 3 ? 1 : h.cfg.perceptual, only_frame ? 1 : 0, D);
   h.launches += 1;
   APV_CUDA_TRY(cudaGetLastError());
   return OK;

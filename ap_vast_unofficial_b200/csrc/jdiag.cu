@@ -341,6 +341,23 @@ __global__ void symmetrize_kernel(const double* __restrict__ in, double* __restr
   }
 }
 
+// Upper triangle <- transpose of the lower triangle, in place (per zone).  grid (nt, nt, nz), tiles with bx >= by.
+__global__ void mirror_lower_kernel(double* __restrict__ C, int n, int ldn) {
+  __shared__ double t[32][33];
+  if (blockIdx.x < blockIdx.y) return;              // only the tiles on and above the diagonal are written
+  const size_t zo = (size_t)blockIdx.z * n * ldn;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;     // the mirrored (lower) tile
+    t[r][threadIdx.x] = (i < n && j < n) ? C[zo + (size_t)i * ldn + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    if (i < n && j < n && j > i) C[zo + (size_t)i * ldn + j] = t[threadIdx.x][r];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Top-V eigenvalues of the symmetric tridiagonal (dd, ee) by multisection: one CTA per eigenvalue, 256 Sturm counts
 // per pass (7 passes from the Gershgorin interval to working precision instead of 53 bisections).  Count
@@ -1074,6 +1091,25 @@ int ensure_smem(Kern k, size_t bytes) {
   return OK;
 }
 
+// Zt[z][v][i] = Y[z][i][v]  (n x Vp row-major vectors-as-columns -> rows of Zt).  grid (ceil(V/32), ceil(n/32), nz), block (32, 8)
+__global__ void vectors_to_rows_kernel(const double* __restrict__ Y, long long ystride, int Vp, double* __restrict__ Zt,
+                                       int n, int V) {
+  __shared__ double t[32][33];
+  const int z = blockIdx.z;
+  const double* y = Y + (size_t)z * ystride;
+  double* o = Zt + (size_t)z * V * n;
+  const int v0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, v = v0 + threadIdx.x;
+    t[r][threadIdx.x] = (i < n && v < V) ? y[(size_t)i * Vp + v] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int v = v0 + r, i = i0 + threadIdx.x;
+    if (v < V && i < n) o[(size_t)v * n + i] = t[threadIdx.x][r];
+  }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1129,7 +1165,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv, ws.q1agg};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
@@ -1170,6 +1206,38 @@ static int trsm_lower(JdiagWs& ws, double* X, double* Y, int m, int ldx, long lo
       u.B = Y + (size_t)s0 * ldx; u.ldb = ldx; u.strideB = strideX;
       u.C = X + (size_t)s1 * ldx; u.ldc = ldx; u.strideC = strideX;
       u.M = n - s1; u.N = m; u.K = rows; u.alpha = -1.0; u.beta = 1.0;
+      APV_TRY(gemm_f64(u, st));
+      ++*launches;
+    }
+  }
+  return OK;
+}
+
+// U = L^-T Q for MANY vectors (V > n / 8): blocked back substitution on super-blocks of SB rows with the explicit
+// inverses of the diagonal super-blocks, bottom to top:  Y_s = Linv_ss^T X_s,  X[0:s0, :] -= L[s, 0:s0]^T Y_s.
+// X (n x Vp, iv slot 4) is destroyed, Y (iv slot 0) receives U; all O(n^2 V) work is DMMA GEMM.
+static int backsolve_gemm(JdiagWs& ws, cudaStream_t st, int* launches) {
+  const int n = ws.n, ldn = ws.ldn, Vp = ws.Vp, nsb = ceil_div(n, SB);
+  double* X = ws.iv + 4 * (size_t)n * Vp;
+  double* Y = ws.iv;
+  const long long xs = 6LL * n * Vp, mstride = (long long)n * ldn;
+  for (int s = nsb - 1; s >= 0; --s) {
+    const int s0 = s * SB, s1 = std::min(n, s0 + SB), rows = s1 - s0;
+    GemmArgs g{};
+    g.batch = ws.nz;
+    g.A = ws.SBinv + (size_t)s * SB * SB; g.lda = SB; g.strideA = (long long)nsb * SB * SB; g.transA = 1;
+    g.B = X + (size_t)s0 * Vp; g.ldb = Vp; g.strideB = xs;
+    g.C = Y + (size_t)s0 * Vp; g.ldc = Vp; g.strideC = xs;
+    g.M = rows; g.N = Vp; g.K = rows; g.alpha = 1.0; g.beta = 0.0;
+    APV_TRY(gemm_f64(g, st));
+    ++*launches;
+    if (s0 > 0) {
+      GemmArgs u{};
+      u.batch = ws.nz;
+      u.A = ws.Lm + (size_t)s0 * ldn; u.lda = ldn; u.strideA = mstride; u.transA = 1;     // L[s0:s1, 0:s0]^T
+      u.B = Y + (size_t)s0 * Vp; u.ldb = Vp; u.strideB = xs;
+      u.C = X; u.ldc = Vp; u.strideC = xs;
+      u.M = s0; u.N = Vp; u.K = rows; u.alpha = -1.0; u.beta = 1.0;
       APV_TRY(gemm_f64(u, st));
       ++*launches;
     }
@@ -1242,13 +1310,43 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     sb_inv_kernel<<<dim3(ceil_div(n, SB), nz), 256, sism, st>>>(ws.Lm, ws.Dinv, ws.SBinv, n, ldn, nblk);
     ++nl;
   }
-  APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = L^-1 A
+  APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = X = L^-1 A (all of it: n^3)
   dim3 tb(32, 8), tg(ceil_div(n, 32), ceil_div(n, 32), nz);
-  transpose_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);                // Cm = A L^-T
-  ++nl;
-  APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = L^-1 A L^-T
-  symmetrize_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);
-  ++nl;
+  if (getenv("APV_REDUCE_FULL")) {          // round-1 form: a second full solve around a transpose (2 n^3 in all)
+    transpose_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);                // Cm = A L^-T
+    ++nl;
+    APV_TRY(trsm_lower(ws, ws.Cm, ws.Tm, n, ldn, mstride, st, &nl));          // Tm = L^-1 A L^-T
+    symmetrize_kernel<<<tg, tb, 0, st>>>(ws.Tm, ws.Cm, n, ldn);
+    ++nl;
+  } else {
+    // C = X L^-T is symmetric: only its lower block triangle is formed, column super-block by column super-block
+    //   C[s0:, s] = X[s0:, s] Linv_ss^T,   X[s1:, s1:] -= C[s1:, s] L[s1:, s]^T  (lower tiles only),
+    // n^3 / 3 instead of n^3 flops and no transpose; the upper triangle is mirrored.
+    const int nsb = ceil_div(n, SB);
+    for (int s0 = 0; s0 < n; s0 += SB) {
+      const int s1 = std::min(n, s0 + SB), rows = s1 - s0;
+      GemmArgs g{};
+      g.batch = nz;
+      g.A = ws.Tm + (size_t)s0 * ldn + s0; g.lda = ldn; g.strideA = mstride;
+      g.B = ws.SBinv + (size_t)(s0 / SB) * SB * SB; g.ldb = SB; g.strideB = (long long)nsb * SB * SB; g.transB = 1;
+      g.C = ws.Cm + (size_t)s0 * ldn + s0; g.ldc = ldn; g.strideC = mstride;
+      g.M = n - s0; g.N = rows; g.K = rows; g.alpha = 1.0; g.beta = 0.0;
+      APV_TRY(gemm_f64(g, st));
+      ++nl;
+      if (s1 < n) {
+        GemmArgs u{};
+        u.batch = nz;
+        u.A = ws.Cm + (size_t)s1 * ldn + s0; u.lda = ldn; u.strideA = mstride;
+        u.B = ws.Lm + (size_t)s1 * ldn + s0; u.ldb = ldn; u.strideB = mstride; u.transB = 1;
+        u.C = ws.Tm + (size_t)s1 * ldn + s1; u.ldc = ldn; u.strideC = mstride;
+        u.M = n - s1; u.N = n - s1; u.K = rows; u.alpha = -1.0; u.beta = 1.0; u.tri = 1;
+        APV_TRY(gemm_f64(u, st));
+        ++nl;
+      }
+    }
+    mirror_lower_kernel<<<tg, tb, 0, st>>>(ws.Cm, n, ldn);
+    ++nl;
+  }
 
   APV_CUDA_TRY(cudaEventRecord(ws.ev[2], st));
   // ---- blocked Householder tridiagonalisation of Cm
@@ -1286,7 +1384,10 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   }
   eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
   const size_t ivsm = (size_t)6 * n * sizeof(double) + (size_t)round_up(n, 16);
-  if (ivsm <= 220 * 1024) {
+  // many vectors (full-spectrum requests): one LANE per vector fills the chip; few vectors: one CTA per vector with the
+  // work arrays in shared memory (one CTA per SM, V / 148 waves of ~2.3 ms at n = 4096)
+  const bool many = (long long)V * nz >= 2048 && !getenv("APV_EIG_FEW");
+  if (ivsm <= 220 * 1024 && !many) {
     APV_TRY(ensure_smem(eig_invit_smem_kernel, ivsm));
     eig_invit_smem_kernel<<<dim3(V, nz), 128, ivsm, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
   } else {
@@ -1294,6 +1395,21 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   }
   eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
   APV_CUDA_TRY(cudaEventRecord(ws.ev[4], st));
+  const bool gemm_bt = two_stage && many && n >= 512;
+  if (gemm_bt) {
+    // full-spectrum back-transformation on the tensor cores: Q2 wavefront, Q1 and U = L^-T Q as GEMMs on the n x Vp
+    // matrix of vectors, then one transpose into the rows of Zt
+    APV_TRY(twostage_apply_q2(ws, st, &nl));
+    APV_TRY(twostage_apply_q1_gemm(ws, st, &nl));
+    APV_CUDA_TRY(cudaEventRecord(ws.ev[5], st));
+    APV_TRY(backsolve_gemm(ws, st, &nl));
+    vectors_to_rows_kernel<<<dim3(ceil_div(V, 32), ceil_div(n, 32), nz), dim3(32, 8), 0, st>>>(ws.iv, 6LL * n * ws.Vp, ws.Vp, ws.Zt, n, V);
+    nl += 6;
+    APV_CUDA_TRY(cudaEventRecord(ws.ev[6], st));
+    APV_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += nl;
+    return OK;
+  }
   if (two_stage) {
     APV_TRY(twostage_apply_q2(ws, st, &nl));
     APV_TRY(twostage_apply_q1(ws, st, &nl));

@@ -47,6 +47,61 @@ __global__ void __launch_bounds__(256) sweep_prefix_kernel(const double* __restr
   }
 }
 
+// The sweep for a LIST of mu in one launch (BASELINE cfg-4): W[k][zone][v][i] = sum_{u<=v} c_u / (lam_u + mu_k) U[u][i].
+// grid (ceil(n / 64), nz, n_mu), 256 threads = 64 columns i x 4 rank segments: a thread first sums its segment, the
+// segment totals are exchanged through shared memory, then the segment is walked again with its offset and written
+// (U is read twice, W written once: ~3 V n 8 bytes per mu and zone, all coalesced 512-byte rows).
+__global__ void __launch_bounds__(256) sweep_multi_kernel(const double* __restrict__ U, const double* __restrict__ cbuf,
+                                                          const double* __restrict__ lam, const double* __restrict__ mu,
+                                                          double* __restrict__ W, int n, int V, int zone0, int zone1) {
+  extern __shared__ double av[];                  // a[v] = c_v / (lam_v + mu), V doubles, then 4 x 64 segment totals
+  double* tot = av + V;
+  const int zi = blockIdx.y, k = blockIdx.z;
+  const int zone = zi == 0 ? zone0 : zone1;
+  const double m = mu[k];
+  for (int v = threadIdx.x; v < V; v += blockDim.x) av[v] = cbuf[(size_t)zi * V + v] / (lam[(size_t)zi * V + v] + m);
+  __syncthreads();
+  const int il = threadIdx.x & 63, seg = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + il;
+  const int slen = (V + 3) / 4, v0 = seg * slen, v1 = min(V, v0 + slen);
+  const double* u = U + (size_t)zi * V * n + i;
+  double acc = 0.0;
+  if (i < n)
+    for (int v = v0; v < v1; ++v) acc = fma(av[v], u[(size_t)v * n], acc);
+  tot[seg * 64 + il] = acc;
+  __syncthreads();
+  if (i >= n) return;
+  acc = 0.0;
+  for (int q = 0; q < seg; ++q) acc += tot[q * 64 + il];
+  double* w = W + (((size_t)k * 2 + zone) * V) * n + i;
+  for (int v = v0; v < v1; ++v) {
+    acc = fma(av[v], u[(size_t)v * n], acc);
+    w[(size_t)v * n] = acc;
+  }
+}
+
+// Eigen-basis figures of merit of the mu x V sweep (BASELINE cfg-4): with U^T (R_D + reg I) U = I and
+// U^T R_B U = Lambda the rank-v filter w = sum_{i<=v} a_i u_i, a_i = c_i / (lambda_i + mu), has
+//   dark energy   w^T (R_D + reg I) w = sum a_i^2,   bright energy  w^T R_B w = sum lambda_i a_i^2,   w^T r_B = sum a_i c_i.
+// out[k][zone][v][3] for mu_k.   grid (n_mu, nz); the prefix over the ranks is sequential (V terms, one thread).
+__global__ void sweep_metrics_kernel(const double* __restrict__ cbuf, const double* __restrict__ lam,
+                                     const double* __restrict__ mu, double* __restrict__ out, int V, int zone0, int zone1) {
+  const int k = blockIdx.x, zi = blockIdx.y;
+  const int zone = zi == 0 ? zone0 : zone1;
+  if (threadIdx.x != 0) return;
+  const double m = mu[k];
+  double dark = 0.0, bright = 0.0, cross = 0.0;
+  double* o = out + (((size_t)k * 2 + zone) * V) * 3;
+  for (int v = 0; v < V; ++v) {
+    const double c = cbuf[(size_t)zi * V + v], l = lam[(size_t)zi * V + v];
+    const double a = c / (l + m);
+    dark = fma(a, a, dark);
+    bright = fma(l * a, a, bright);
+    cross = fma(a, c, cross);
+    o[3 * v] = dark; o[3 * v + 1] = bright; o[3 * v + 2] = cross;
+  }
+}
+
 // S7 for the controlled streams.  grid (H / RT, V, nz), 256 threads.  A CTA renders a tile of RT hop positions (and
 // the Nb/H - 1 overlap positions behind each of them) of ALL loudspeakers of one (zone, rank): lane = hop position, so
 // the overlap buffer is read and written with unit stride and the tap loop reads the filter by broadcast; every warp
@@ -174,6 +229,36 @@ int stage_sweep(Handle& h, double mu, double* W_out) {
   sweep_dot_kernel<<<dim3(D.V, h.nz), 256, 0, h.st>>>(h.jd.Zt, h.rvec, cbuf, D.n, D.V, h.zones[0], h.zones[1]);
   sweep_prefix_kernel<<<dim3(ceil_div(D.n, 256), h.nz), 256, D.V * sizeof(double), h.st>>>(
       h.jd.Zt, cbuf, h.jd.lam, W_out, mu, D.n, D.V, h.zones[0], h.zones[1]);
+  h.launches += 2;
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
+// filters for n_mu values of mu (device array) into W_out (n_mu, 2, V, n); c = U^T r is formed once
+int stage_sweep_multi(Handle& h, int n_mu, const double* d_mu, double* W_out) {
+  const Dims& D = h.D;
+  if (h.nz == 0) return OK;
+  double* cbuf = h.jd.colbuf;
+  sweep_dot_kernel<<<dim3(D.V, h.nz), 256, 0, h.st>>>(h.jd.Zt, h.rvec, cbuf, D.n, D.V, h.zones[0], h.zones[1]);
+  const size_t sm = (size_t)(D.V + 256) * sizeof(double);
+  static PerDevice pd_configured; size_t& configured = pd_configured.cur();
+  if (sm > 48 * 1024 && sm > configured) {
+    APV_CUDA_TRY(cudaFuncSetAttribute(sweep_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    configured = sm;
+  }
+  sweep_multi_kernel<<<dim3(ceil_div(D.n, 64), h.nz, n_mu), 256, sm, h.st>>>(h.jd.Zt, cbuf, h.jd.lam, d_mu, W_out, D.n, D.V,
+                                                                             h.zones[0], h.zones[1]);
+  h.launches += 2;
+  APV_CUDA_TRY(cudaGetLastError());
+  return OK;
+}
+
+int stage_sweep_metrics(Handle& h, int n_mu, const double* d_mu, double* d_out) {
+  const Dims& D = h.D;
+  if (h.nz == 0) return OK;
+  double* cbuf = h.jd.colbuf;
+  sweep_dot_kernel<<<dim3(D.V, h.nz), 256, 0, h.st>>>(h.jd.Zt, h.rvec, cbuf, D.n, D.V, h.zones[0], h.zones[1]);
+  sweep_metrics_kernel<<<dim3(n_mu, h.nz), 32, 0, h.st>>>(cbuf, h.jd.lam, d_mu, d_out, D.V, h.zones[0], h.zones[1]);
   h.launches += 2;
   APV_CUDA_TRY(cudaGetLastError());
   return OK;

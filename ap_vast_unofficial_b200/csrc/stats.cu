@@ -9,6 +9,8 @@
 // buffered) and the FP64 tensor-core fragments (mma.sync m8n8k4 = SASS DMMA.8x8x4) are gathered
 // from them by index arithmetic: A[row][k] = seg[(J-1-i) + k].  Only lower-triangle tiles are
 // computed; the epilogue mirrors them so R is stored as a full symmetric matrix.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "engine.cuh"
@@ -19,6 +21,7 @@ namespace {
 
 constexpr int TM = 128;      // CTA tile (rows = cols)
 constexpr int KC = 64;       // K chunk per pipeline stage
+constexpr int FLUSH_CHUNKS = 4;   // DMMA accumulators are flushed into the shared-memory totals every 4 chunks (256 terms)
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier transaction counting: one elected thread stages the
 // 1-D segments of a pipeline stage; the copy engine fills shared memory while all warps issue DMMAs.
@@ -71,11 +74,14 @@ __global__ void pack_stats_kernel(const double* __restrict__ S, double* __restri
 // plus one zero segment used by out-of-range rows.
 __global__ void __launch_bounds__(256, 1)
 syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, Dims D, int ntile, int SEG, int maxl,
-                     unsigned path_mask, int m_first, int m_count) {
+                     unsigned path_mask, int m_first, int m_count, int comp) {
   // blockIdx.z = microphone slice: the K dimension (microphones x P) is split per microphone and the per-microphone
   // partial matrices are added up by a tree (syrk_reduce_kernel) -- a fixed-order accumulation over all M P terms
   // would leave R with ~1e-14 relative rounding error, which the ill-conditioned pencil amplifies beyond the
-  // 1e-8 filter-parity bar at n = 4096.
+  // 1e-8 filter-parity bar at n = 4096.  Inside a microphone the DMMA accumulators only ever hold FLUSH_CHUNKS * KC
+  // terms: they are then added into a per-thread total kept in shared memory ([64][256] doubles, and with `comp` a
+  // float compensation term per entry that collects the rounding errors of those additions, TwoSum), so the
+  // sequential part of every sum is 256 terms long instead of P.
   const int path = blockIdx.y;
   if (!((path_mask >> path) & 1u)) return;
   const int mslice = blockIdx.z;
@@ -91,6 +97,8 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
   // stage layout: [row segs: maxl*SEG][col segs: maxl*SEG], two stages, then zero segment
   const int stage_sz = 2 * maxl * SEG;
   double* zero_seg = sm + 2 * stage_sz;
+  double* tot = zero_seg + SEG;                                   // [64][256] running totals, entry-major
+  float* tlo = reinterpret_cast<float*>(tot + 64 * 256);          // [64][256] compensation (comp != 0)
   __shared__ __align__(8) unsigned long long full_bar[2];
   for (int i = threadIdx.x; i < SEG; i += blockDim.x) zero_seg[i] = 0.0;
   if (threadIdx.x == 0) {
@@ -135,6 +143,7 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
 
   const int nchunk = (P + KC - 1) / KC;
   const int nit = nchunk;                                       // one microphone per CTA
+  bool flushed = false;
   const size_t chan_stride = (size_t)D.Ns;
   const double* base = Sp + ((size_t)path * D.M + m_first + mslice) * L * chan_stride;
 
@@ -177,6 +186,38 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
       for (int rt = 0; rt < 8; ++rt)
 #pragma unroll
         for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
+    }
+    // (flushing the warps of an SM sub-partition in different chunks was measured and is slower: every chunk ends in a
+    // CTA barrier, so the chunk lasts as long as its slowest warp -- 70.3 instead of 64.1 ms per block at cfg-3)
+    if (comp >= 0 && ((it % FLUSH_CHUNKS) == FLUSH_CHUNKS - 1 || it == nit - 1)) {
+      const bool first = !flushed;
+      const bool last = it == nit - 1;
+      flushed = true;
+#pragma unroll
+      for (int rt = 0; rt < 8; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int e = ((rt * 4 + ct) * 2 + q) * 256 + tid;
+            const double x = acc[rt][ct][q];
+            double hi = x, lo = 0.0;
+            if (!first) {
+              const double t0 = tot[e];
+              hi = t0 + x;
+              if (comp > 0) {
+                const double bb = hi - t0;
+                lo = (double)tlo[e] + ((t0 - (hi - bb)) + (x - bb));     // TwoSum: exact rounding error of t0 + x
+              }
+            }
+            if (last) {
+              acc[rt][ct][q] = hi + lo;
+            } else {
+              tot[e] = hi;
+              if (comp > 0) tlo[e] = (float)lo;
+              acc[rt][ct][q] = 0.0;
+            }
+          }
     }
   }
 
@@ -464,8 +505,17 @@ int stage_stats(Handle& h) {
   const int ntile = nt * (nt + 1) / 2;
   const int SEG = round_up(D.J + KC - 1, 2);
   const int maxl = min(D.L, (TM - 1) / D.J + 2);
-  const size_t sm = (size_t)(4 * maxl * SEG + SEG) * sizeof(double);
-  if (sm > 220 * 1024) {
+  const size_t stage_sm = (size_t)(4 * maxl * SEG + SEG) * sizeof(double);
+  const size_t tot_sm = (size_t)64 * 256 * sizeof(double), lo_sm = (size_t)64 * 256 * sizeof(float);
+  // 1: chunk totals + compensation terms; 0: totals only; -1: the staging of a very short filter leaves no room
+  // (the accumulators then run over the whole microphone as in round 1)
+  // The compensation terms cost 4 ms per block at cfg-3 for a parity gain that the tests cannot resolve (the totals
+  // alone bring the worst cfg-3 filter error from 7.2e-9 to ~2e-9, the reference's own rounding floor is 1.1e-9):
+  // they are opt-in (APV_SYRK_COMP=1).
+  static const bool want_comp = getenv("APV_SYRK_COMP") && atoi(getenv("APV_SYRK_COMP")) > 0;
+  const int comp = (want_comp && stage_sm + tot_sm + lo_sm <= 224 * 1024) ? 1 : (stage_sm + tot_sm <= 224 * 1024 ? 0 : -1);
+  const size_t sm = stage_sm + (comp >= 0 ? tot_sm : 0) + (comp > 0 ? lo_sm : 0);
+  if (sm > 224 * 1024) {
     snprintf(g_err, sizeof(g_err), "stats_syrk: filter_length %d too small for the tile staging (%zu B smem)", D.J, sm);
     return EINVAL_;
   }
@@ -508,7 +558,7 @@ int stage_stats(Handle& h) {
     const int mc = std::min(4, D.M - m0);
     const unsigned mA = m0 < MA ? (pmask & 0x5u) : 0u, mB = pmask & 0xAu;
     if ((mA | mB) == 0u) continue;
-    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc);
+    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc, comp);
     const bool lastA = m0 + 4 >= MA, lastB = m0 + 4 >= D.M;
     if (mA && mB && lastA != lastB) {
       syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mA, mc, m0 == 0, lastA);

@@ -580,6 +580,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra measurement of the structured-statistics mode")
     ap.add_argument("--no-pipeline", action="store_true", help="blocks strictly one after the other (diagnostic)")
+    ap.add_argument("--no-perceptual", action="store_true", help="cfg5: switch the per-zone perceptual weighting off")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

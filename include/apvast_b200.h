@@ -199,6 +199,11 @@ int apv_set_gain_table(apv_handle* h, int n_channels, const double* G2, double C
 /* mu x V trade-off sweep (BASELINE cfg-4): filters for n_mu values of mu from ONE joint diagonalisation.
  * w_out: (n_mu, 2, V, n) host buffer. */
 int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out);
+/* The same sweep without leaving the device: d_w_out = DEVICE buffer (n_mu, 2, V, n) or NULL; metrics_out = host
+ * (n_mu, 2, V, 3) or NULL: per rank v the eigen-basis figures of merit of w[v] -- dark energy w'(R_D + reg I)w = sum a_i^2,
+ * bright energy w'R_B w = sum lambda_i a_i^2 and w'r_B = sum a_i c_i (a_i = c_i / (lambda_i + mu), c = U'r_B); they follow
+ * from U'(R_D + reg I)U = I, U'R_B U = Lambda (jdiag.m:33-35) and pick the operating point of the trade-off. */
+int apv_sweep_device(apv_handle* h, int n_mu, const double* mu, void* d_w_out, double* metrics_out);
 
 /* Evaluation of rendered loudspeaker feeds (callers' side of the path: Matlab/ControlMethods/predictPressure.m:12-17,
  * Matlab/main.m:120-130).  feeds: (n_samples, L) host, signal: (n_samples) programme signal of the zone.

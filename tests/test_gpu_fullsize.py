@@ -96,10 +96,15 @@ def test_cfg3_structured_statistics_equal_dmma(cfg3_run):
     for t in range(4):
         e2.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
     errs = {nm: rel(getattr(e2, nm), getattr(eng, nm)) for nm in ("R_A_to_A", "R_A_to_B", "R_B_to_A", "R_B_to_B")}
-    werr = max(rel(e2.w_A[v], eng.w_A[v]) for v in range(eng.number_of_eigenvectors))
-    print("structured vs DMMA at cfg-3:", errs, "max filter diff", werr)
+    # block 3 is still inside the start transient (random start buffers): the pencil is at its worst there, and a rank
+    # whose eigenvalue gap is small amplifies the 1e-15 difference of the two statistics routes; the bar scales with it
+    lam = eng.lambda_A
+    gap = np.r_[np.abs(np.diff(lam)) / lam[0], 1.0]
+    werr = [rel(e2.w_A[v], eng.w_A[v]) for v in range(eng.number_of_eigenvectors)]
+    print("structured vs DMMA at cfg-3:", errs, "max filter diff", max(werr), "min gap", gap.min())
     assert max(errs.values()) < 1e-12, errs
-    assert werr < 1e-8, werr
+    for v, e in enumerate(werr):
+        assert e < (2e-8 if gap[v] > 1e-6 else 1e-5), (v, e, gap[v])
 
 
 def test_mu_sweep_matches_oracle_rank_loop():
@@ -291,11 +296,12 @@ def test_cfg3_against_reference_golden(stats_mode):
     assert not fails, fails
 
 
-def test_cfg3_second_golden_all_ranks_past_warmup():
+@pytest.mark.parametrize("stats_mode", [0, 2])
+def test_cfg3_second_golden_all_ranks_past_warmup(stats_mode):
     """A second draw of the cfg-3 workload (other RIRs, other programme signals), 8 hops so that four of them are
     fully signal-driven, ALL 64 ranks of those four hops (tests/golden/cfg3_reference_v1.npz)."""
-    worst, fails = _golden_run("cfg3_reference_v1.npz", "cfg3", 0, _BARS)
-    print("cfg3 (variant 1) vs reference golden: worst relative errors", worst, "violations", fails)
+    worst, fails = _golden_run("cfg3_reference_v1.npz", "cfg3", stats_mode, _BARS)
+    print("cfg3 (variant 1) vs reference golden (stats_mode=%d): worst relative errors" % stats_mode, worst, "violations", fails)
     assert not fails, fails
 
 

@@ -150,7 +150,7 @@ def test_experimental_regularization_off_matches_the_oracle():
 def test_filter_longer_than_the_block_is_cropped_like_rfft():
     """filter_length > block_size: the reference's rfft(w, Nb) keeps the first Nb taps (apvast.py:417-420)."""
     from oracle.apvast_oracle import ApvastOracle
-    rA, rB, cfg, sA, sB, nblk, H = _case(L=2, M=2, J=40, K=24, Nb=32, N=96, V=5, nblk=8, seed=12)
+    rA, rB, cfg, sA, sB, nblk, H = _case(L=3, M=2, J=40, K=24, Nb=32, N=96, V=5, nblk=8, seed=12)
     np.random.seed(0); gpu = _engine()(rir_A=rA, rir_B=rB, **cfg)
     np.random.seed(0); o = ApvastOracle(rir_A=rA, rir_B=rB, **cfg)
     for t in range(nblk):
@@ -224,3 +224,39 @@ def test_multizone_per_zone_perceptual_weighting(Z):
             if gap[v] > 1e-9:
                 assert rel(w[v], ora.w[z][v]) < 1e-8, (z, v)
     gpu.close()
+
+
+def test_full_spectrum_path_at_cfg2_size():
+    """V = n = 1024 on both zones: the many-vector route (lane-per-vector inverse iteration, aggregated block-reflector
+    GEMM back-transformation, GEMM back substitution; BASELINE cfg-4 semantics).  Checks: jdiag.m:33-35 identities,
+    the closed form w[V-1] = (R_B + mu (R_D + reg I))^-1 r_B (apVast.m:115-118), the one-launch mu sweep and its
+    eigen-basis figures of merit against direct evaluation."""
+    from ap_vast_unofficial_b200.workloads import make_workload
+    wl = make_workload("cfg2", n_blocks=5)
+    cfg = dict(wl["cfg"]); n = 1024
+    cfg["number_of_eigenvectors"] = n
+    np.random.seed(0)
+    eng = _engine()(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **cfg)
+    H = eng.hop_size
+    for t in range(5):
+        eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+    mus = np.array([0.01, 1.0, 10.0])
+    wA, wB = eng.sweep(mus)
+    met = eng.sweep_metrics(mus)
+    for (RB, RD, U, lam, r, w, zi) in ((eng.R_A_to_A, eng.R_A_to_B, eng.U_A, eng.lambda_A, eng.r_A[:, 0], wA, 0),
+                                       (eng.R_B_to_B, eng.R_B_to_A, eng.U_B, eng.lambda_B, eng.r_B[:, 0], wB, 1)):
+        assert np.all(np.diff(lam) <= 0)
+        Bm = RD + 1e-7 * np.eye(n)
+        assert np.max(np.abs(U.T @ Bm @ U - np.eye(n))) < 1e-8
+        assert np.max(np.abs(U.T @ RB @ U - np.diag(lam))) / lam[0] < 1e-8
+        for k, mu in enumerate(mus):
+            closed = np.linalg.solve(RB + mu * Bm, r)
+            assert rel(w[k, -1], closed) < 1e-9, (zi, k)
+            for v in (0, 17, 500, n - 1):
+                x = w[k, v]
+                assert abs(met[k, zi, v, 0] - x @ Bm @ x) <= 1e-8 * abs(x @ Bm @ x)
+                assert abs(met[k, zi, v, 1] - x @ RB @ x) <= 1e-8 * abs(x @ RB @ x)
+                assert abs(met[k, zi, v, 2] - x @ r) <= 1e-8 * abs(x @ r)
+    # the per-block filters (mu of the constructor) are the same prefix sums
+    assert rel(eng.w_A[:, :, 0], eng.sweep([eng.mu])[0][0]) < 1e-12
+    eng.close()

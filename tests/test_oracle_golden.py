@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle.apvast_oracle import ApvastOracle, jdiag, toeplitz_rows
-from tests._golden import compare_state, replay
+from tests._golden import GOLDEN, compare_state, rel, replay
 
 SMALL = ["tiny", "tiny_hop", "tiny_runA", "tiny_full", "mid"]
 
@@ -108,3 +108,28 @@ def test_multizone_oracle_reduces_to_the_two_zone_oracle():
         wa, wb = np.array(two.w_A)[v, :, 0], np.array(two.w_B)[v, :, 0]
         assert np.linalg.norm(mz.w[0][v] - wa) / np.linalg.norm(wa) < 1e-9
         assert np.linalg.norm(mz.w[1][v] - wb) / np.linalg.norm(wb) < 1e-9
+
+
+def test_oracle_against_cfg2_reference_golden():
+    """The oracle at BASELINE cfg-2 size (n = 1024) against the UNMODIFIED reference (tests/golden/cfg2_reference.npz,
+    oracle/make_golden_cfg3.py --workload cfg2): three hops, all 64 ranks."""
+    import os
+    from ap_vast_unofficial_b200.workloads import make_workload
+    from oracle.apvast_oracle import ApvastOracle
+    z = np.load(os.path.join(GOLDEN, "cfg2_reference.npz"))
+    nblk = 3
+    wl = make_workload("cfg2", n_blocks=int(z["nblk"]))      # (the programme signals are normalised over their whole length)
+    np.random.seed(int(z["seed"]))
+    eng = ApvastOracle(rir_A=wl["rir_A"], rir_B=wl["rir_B"], perceptual=False, **wl["cfg"])
+    H, V = eng.hop_size, eng.number_of_eigenvectors
+    for t in range(nblk):
+        outs = eng.process_input_buffers(wl["signal_A"][t * H:(t + 1) * H], wl["signal_B"][t * H:(t + 1) * H])
+        assert rel(np.diag(eng.R_A_to_B), z[f"R_A_to_B_diag_{t}"]) < 1e-13
+        lam_ref = z[f"lambda_A_{t}"]
+        gap = np.abs(np.diff(lam_ref)) / lam_ref[0]
+        for v in range(V):
+            if gap[v] > 1e-9:
+                assert rel(eng.w_A[v, :, 0], z[f"w_A_{t}"][v]) < 1e-8, (t, v)
+        got, want = np.stack([outs[1][0], outs[1][V - 1]]), z[f"out_B_{t}"]
+        # (hop 0 renders 1e-18: the first input block is still almost all zeros)
+        assert np.linalg.norm(got - want) <= 1e-9 * max(np.linalg.norm(want), 1e-6), t
