@@ -280,9 +280,10 @@ class apvast:
             oB = oB[:, sel] if oB is not None else None
         return (oA, oB, oAt, oBt, w) if want_filters else (oA, oB, oAt, oBt)
 
-    def set_pipeline(self, on: bool):
-        """Overlap of S1-S4 of hop t+1 with S5-S7 of hop t in multi-hop calls (default on; results are identical)."""
-        capi.check(capi.lib().apv_set_pipeline(self._h, int(bool(on))))
+    def set_pipeline(self, mode):
+        """Overlap of S1-S4 of hop t+1 with S5-S7 of hop t in multi-hop calls: 0 / False off, 1 from the start of S5,
+        2 / True (default) from the bulge chasing of hop t on.  Results are identical."""
+        capi.check(capi.lib().apv_set_pipeline(self._h, 2 if mode is True else int(mode)))
 
     def advance_state(self, input_A, input_B):
         """S1-S3 only (state update without statistics/filters/rendering): warm-up of a block range."""

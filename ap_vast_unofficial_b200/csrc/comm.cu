@@ -230,9 +230,9 @@ int apv_range_run(apv_handle* h, int n_halo, int n_owned, const double* in_A, co
   auto own = [&](const double* base, int b) { return base + (size_t)(n_halo + b) * D.H; };
   if (n_owned > 0) APV_TRY(enqueue_front(*h, 0, own(dA, 0), own(dB, 0), false));
   for (int b = 0; b < n_owned; ++b) {
-    if (b + 1 < n_owned) APV_TRY(enqueue_front(*h, b + 1, own(dA, b + 1), own(dB, b + 1), false));
     const BlockSink sink{h->rg_out + (size_t)b * per_out(D), nullptr, h->rg_w + (size_t)b * per_w(D), h->rg_info + (size_t)b * 8};
     APV_TRY(enqueue_back(*h, b, sink));
+    if (b + 1 < n_owned) APV_TRY(enqueue_front(*h, b + 1, own(dA, b + 1), own(dB, b + 1), false));
   }
   h->rg_owned = n_owned;
   return leave_multiblock(*h);

@@ -225,8 +225,12 @@ bool pipelined(const Handle& h) {
 // Multi-block calls run every block in two halves.  With pipelining the front half (S1-S4) goes to the low-priority
 // stream and fills slot b & 1 of the statistics while the back half (S5-S7) of block b - 1 still runs on the main
 // stream: S4 of block b + 1 depends on the streaming state only (apvast.py:329-364), never on the filters of block b.
-// The caller enqueues front(b + 1) BEFORE back(b), so that the few launches of a front half are never stuck behind
-// the ~900 launches of a back half in the host's submission order.  `b` counts from 0 inside the call.
+// Measured at cfg-3 (profiles/r02_pipeline_timeline_v1.txt): when the front half starts together with the back half,
+// the ~900 short launches of S5 keep waiting for SMs held by SYRK CTAs and the overlap gains only 5 %.  With
+// pipeline == 2 (default) the front half of block b + 1 is therefore gated on the START OF THE BULGE CHASING of block
+// b (event ev2[0] of the two-stage tridiagonalisation): from there on S5 is a handful of latency-bound kernels that
+// leave most SMs idle, and the statistics fill them.  The caller enqueues back(b) BEFORE front(b + 1) so that the
+// event is recorded when the wait is enqueued.  `b` counts from 0 inside the call.
 int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only) {
   const int slot = (int)(b & 1);
   const bool pipe = pipelined(h) && !state_only;
@@ -242,6 +246,8 @@ int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, b
       APV_CUDA_TRY(cudaEventRecord(h.ev_free[1], main_st));                  // state written by earlier calls
       APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[1], 0));
     }
+    if (b >= 1 && h.pipeline == 2 && h.nz > 0 && h.jd.last_two_stage)
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.jd.ev2[0], 0));         // block b - 1 has reached its bulge chasing
     h.st = h.st_front;
   }
   if (h.dbg_ev && !state_only && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 0], h.st);
@@ -395,7 +401,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   for (auto& e : h->ev_d2h) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   {
     const char* pe = getenv("APV_PIPELINE");
-    h->pipeline = pe ? atoi(pe) : 1;
+    h->pipeline = pe ? atoi(pe) : 2;
   }
   for (auto& e : h->ev_syrk) CUB(cudaEventCreate(&e));
   for (auto& e : h->ev_timer) CUB(cudaEventCreate(&e));
@@ -594,11 +600,11 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   for (long b = 0; b < nblocks && rc == OK; ++b) {
     const int rs = (int)(b % cap);
     double* slot = h->ring + (size_t)rs * sd;
-    if (b + 1 < nblocks) rc = enqueue_front(*h, b + 1, sig_ptr(0, b + 1), sig_ptr(1, b + 1), false);
     if (b >= cap) cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
     BlockSink sink{slot, slot + 2 * per, slot + 2 * per + 2 * (size_t)D.H,
                    reinterpret_cast<int*>(slot + 2 * per + 2 * (size_t)D.H + perw)};
     if (rc == OK) rc = enqueue_back(*h, b, sink);
+    if (rc == OK && b + 1 < nblocks) rc = enqueue_front(*h, b + 1, sig_ptr(0, b + 1), sig_ptr(1, b + 1), false);
     cu(cudaEventRecord(h->ev_rend[rs], h->st), "record");
     cu(cudaStreamWaitEvent(h->st_copy, h->ev_rend[rs], 0), "wait render");
     cu(cudaMemcpyAsync(h->ring_pin + (size_t)rs * sd, slot, sd * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy), "D2H");
@@ -700,7 +706,7 @@ int apv_debug_timeline(apv_handle* h, int nblocks, float* ms) {
 
 int apv_set_pipeline(apv_handle* h, int on) {
   if (!h) return fail(EINVAL_, "null argument");
-  h->pipeline = on != 0;
+  h->pipeline = on < 0 ? 0 : (on > 2 ? 2 : on);
   return OK;
 }
 

@@ -145,8 +145,9 @@ int apv_finish_block(apv_handle* h, double* out_A, double* out_B, double* out_A_
 /* Warm-up only: S1-S3 (state update) without statistics / filters / rendering (multi-GPU halo). */
 int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B);
 
-/* 0: consecutive blocks of a multi-block call strictly in order on one stream; 1 (default, also env APV_PIPELINE):
- * S1-S4 of block t+1 overlap S5-S7 of block t.  Results are bit-identical either way. */
+/* 0: consecutive blocks of a multi-block call strictly in order on one stream; 1: S1-S4 of block t+1 start together
+ * with S5-S7 of block t; 2 (default, also env APV_PIPELINE): they start when block t reaches its bulge chasing, the
+ * point from which S5 leaves most SMs idle.  Results are bit-identical in all three. */
 int apv_set_pipeline(apv_handle* h, int on);
 /* Diagnostic timeline of a multi-block call: arm with ms == NULL, run, read back (nblocks, 4) milliseconds
  * (front start, front end, back start, back end per block, relative to the first event). */
