@@ -38,6 +38,7 @@ class apvast_zones:
         if any(r.shape != rirs[0].shape for r in rirs):
             raise RuntimeError("rirs of unequal size")
         self.perceptual = bool(engine_kwargs.pop("perceptual", False))
+        concurrent = bool(engine_kwargs.pop("concurrent", True))
         K, L, M = rirs[0].shape
         Z = len(rirs)
         self.n_zones, self.number_of_eigenvectors = Z, int(number_of_eigenvectors)
@@ -52,6 +53,8 @@ class apvast_zones:
         self.hop_size = self.engines[0].hop_size
         self._silence = np.zeros(self.hop_size)
         self._M = M
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=Z if concurrent else 1)
 
     def _exchange_weights(self):
         from . import _capi as capi
@@ -65,12 +68,15 @@ class apvast_zones:
     def process_input_buffers(self, inputs):
         if len(inputs) != self.n_zones:
             raise RuntimeError("invalid input size")
+        # The Z engines are independent and each owns its CUDA streams: one host thread per engine (ctypes releases the
+        # GIL) lets the latency-bound phases of one zone's joint diagonalisation (bulge chasing, eigenvectors) run
+        # beside the tensor-core phases of the others instead of one zone after the other.
         if not self.perceptual:
-            return [eng.process_input_buffers(x, self._silence)[0] for eng, x in zip(self.engines, inputs)]
-        for eng, x in zip(self.engines, inputs):
-            eng._begin(x, self._silence)
+            return list(self._pool.map(lambda ex: ex[0].process_input_buffers(ex[1], self._silence)[0],
+                                       zip(self.engines, inputs)))
+        list(self._pool.map(lambda ex: ex[0]._begin(ex[1], self._silence), zip(self.engines, inputs)))
         self._exchange_weights()
-        return [eng._finish()[0] for eng in self.engines]
+        return list(self._pool.map(lambda e: e._finish()[0], self.engines))
 
     @property
     def w(self):
@@ -89,5 +95,6 @@ class apvast_zones:
         return [eng.stage_times() for eng in self.engines]
 
     def close(self):
+        self._pool.shutdown(wait=True)
         for e in self.engines:
             e.close()

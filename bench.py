@@ -84,7 +84,8 @@ def workload_config(args, sh, world):
                         f"K={sh['K']} Nb={sh['Nb']} H={sh['H']} N={sh['N']} V={sh['V']} fs=48000",
             "sharding": f"contiguous block ranges over {world} rank(s): S1-S3 halo replay, overlap-add tail "
                         f"ncclSend/ncclRecv, gather to rank 0",
-            "l2": "per-block working set ~1.6 GB (4 R + jdiag workspace) >> 126 MB L2; no explicit flush"}
+            "l2": f"per-block working set ~{16 * sh['n'] ** 2 * 8 / 1e6:.0f} MB (2 x 4 statistics matrices + the joint-"
+                  f"diagonalisation workspace) against 126 MB of L2; no explicit flush"}
 
 
 class ClockSampler:
