@@ -51,6 +51,7 @@ SIGNATURES = {
     "apv_finish_block": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "apv_advance_state": (C.c_int, [C.c_void_p, _dp, _dp]),
     "apv_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "apv_set_depth": (C.c_int, [C.c_void_p, C.c_int]),
     "apv_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "apv_set_reg_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "apv_copy_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),

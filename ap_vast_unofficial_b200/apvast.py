@@ -285,6 +285,10 @@ class apvast:
         2 / True (default) from the bulge chasing of hop t on.  Results are identical."""
         capi.check(capi.lib().apv_set_pipeline(self._h, 2 if mode is True else int(mode)))
 
+    def set_depth(self, depth: int):
+        """Joint diagonalisations in flight in multi-hop calls (1 or 2; default 2 for n < 2048).  Results are identical."""
+        capi.check(capi.lib().apv_set_depth(self._h, int(depth)))
+
     def advance_state(self, input_A, input_B):
         """S1-S3 only (state update without statistics/filters/rendering): warm-up of a block range."""
         if self._mode in (2, 3):

@@ -199,6 +199,7 @@ int apv_range_reserve(apv_handle* h, int max_halo, int max_owned, int total_on_r
   if (!h || max_owned < 1 || max_halo < 0 || total_on_root < 0) return fail(EINVAL_, "bad argument");
   DevGuard dg(h->device);
   APV_TRY(range_alloc(*h, max_owned, total_on_root));
+  APV_TRY(ensure_depth(*h, -1));
   const size_t need = 2 * (size_t)(max_halo + max_owned) * h->D.H;
   if (need > h->rg_sig_cap) {
     if (h->rg_sig) cudaFree(h->rg_sig);

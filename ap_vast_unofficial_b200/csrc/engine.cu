@@ -151,10 +151,13 @@ int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1,
 }
 
 // Back half: S5 (joint diagonalisation of the current slot), S6 (filter sum into h.W), S7 (rendering into h.d_out).
-int run_back(Handle& h) {
+int run_back(Handle& h, cudaEvent_t order) {
   cudaEvent_t* ev = h.ev;
   APV_CUDA_TRY(cudaEventRecord(ev[7], h.st));
   APV_TRY(run_jdiag(h));
+  // with two back halves in flight the joint diagonalisations overlap, but S6 / S7 touch sequential state (the
+  // published eigenpairs, the output overlap buffers G): they follow the previous block's
+  if (order) APV_CUDA_TRY(cudaStreamWaitEvent(h.st, order, 0));
   APV_TRY(publish_eig(h));
   APV_CUDA_TRY(cudaEventRecord(ev[4], h.st));
   APV_TRY(stage_sweep(h, h.cfg.mu, h.W));
@@ -232,22 +235,26 @@ bool pipelined(const Handle& h) {
 // leave most SMs idle, and the statistics fill them.  The caller enqueues back(b) BEFORE front(b + 1) so that the
 // event is recorded when the wait is enqueued.  `b` counts from 0 inside the call.
 int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only) {
-  const int slot = (int)(b & 1);
+  const int slot = (int)(b % Handle::NSLOT);
   const bool pipe = pipelined(h) && !state_only;
+  const bool two = pipe && h.depth == 2;
   cudaStream_t main_st = h.st;
   h.launches_front = 0;
   const int saved = h.launches;
   h.launches = 0;
   use_slot(h, slot);
   if (pipe) {
-    if (b >= 2) {
-      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[slot], 0));     // back half of block b - 2 released the slot
+    if (b >= Handle::NSLOT) {
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[slot], 0));     // back half of block b - 3 released the slot
     } else if (b == 0) {
-      APV_CUDA_TRY(cudaEventRecord(h.ev_free[1], main_st));                  // state written by earlier calls
-      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[1], 0));
+      APV_CUDA_TRY(cudaEventRecord(h.ev_join, main_st));                     // state written by earlier calls
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_join, 0));
+      if (two) APV_CUDA_TRY(cudaStreamWaitEvent(h.st_back2, h.ev_join, 0));
     }
-    if (b >= 1 && h.pipeline == 2 && h.nz > 0 && h.jd.last_two_stage)
+    if (b >= 1 && h.pipeline == 2 && !two && h.nz > 0 && h.jd.last_two_stage)
       APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.jd.ev2[0], 0));         // block b - 1 has reached its bulge chasing
+    if (b >= 2 && !two)
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[(b - 2) % Handle::NSLOT], 0));   // depth 1: at most one block ahead
     h.st = h.st_front;
   }
   if (h.dbg_ev && !state_only && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 0], h.st);
@@ -261,31 +268,58 @@ int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, b
   return OK;
 }
 
-// Back half of block b; results go to the device buffers of `sink`.
-int enqueue_back(Handle& h, long b, const BlockSink& sink) {
-  const int slot = (int)(b & 1);
+// Back half of block b; results go to the device buffers of `sink`; `done` (optional) is recorded behind it.
+// depth 2 (default for n < 2048, where S5 is latency-bound and leaves most of the chip idle): the back halves of
+// consecutive blocks alternate between two streams and two joint-diagonalisation workspaces, so two S5 run side by
+// side; S6 / S7 stay in block order (ev_order).
+int enqueue_back(Handle& h, long b, const BlockSink& sink, cudaEvent_t done) {
+  const int slot = (int)(b % Handle::NSLOT);
   const bool pipe = pipelined(h);
+  const bool two = pipe && h.depth == 2;
+  const int which = two ? (int)(b & 1) : 0;
   cudaStream_t main_st = h.st;
+  cudaStream_t sb = which ? h.st_back2 : main_st;
   use_slot(h, slot);
   h.launches = h.launches_front;
-  if (pipe) APV_CUDA_TRY(cudaStreamWaitEvent(main_st, h.ev_ready[slot], 0));
+  if (pipe) APV_CUDA_TRY(cudaStreamWaitEvent(sb, h.ev_ready[slot], 0));
   h.W = sink.W ? sink.W : h.home_W;
   h.d_out = sink.out ? sink.out : h.home_out;
   h.d_out_t = sink.out_t ? sink.out_t : h.home_out_t;
-  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 2], main_st);
-  int rc = run_back(h);
-  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 3], main_st);
+  if (which) std::swap(h.jd, h.jd2);
+  h.st = sb;
+  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 2], sb);
+  int rc = run_back(h, (two && b >= 1) ? h.ev_order : nullptr);
+  if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 3], sb);
+  if (rc == OK && two) rc = cudaEventRecord(h.ev_order, sb) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
   if (rc == OK && sink.info && h.nz > 0)
-    rc = cudaMemcpyAsync(sink.info, h.jd.info, (size_t)h.nz * 4 * sizeof(int), cudaMemcpyDeviceToDevice, main_st) == cudaSuccess
+    rc = cudaMemcpyAsync(sink.info, h.jd.info, (size_t)h.nz * 4 * sizeof(int), cudaMemcpyDeviceToDevice, sb) == cudaSuccess
              ? OK : fail(ECUDA, "status copy failed");
-  if (rc == OK && pipe) rc = cudaEventRecord(h.ev_free[slot], main_st) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
+  if (rc == OK && pipe) rc = cudaEventRecord(h.ev_free[slot], sb) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
+  if (rc == OK && done) rc = cudaEventRecord(done, sb) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
+  h.st = main_st;
+  if (which) std::swap(h.jd, h.jd2);
+  h.last_ws = which;
   return rc;
+}
+
+// Two back halves in flight need a second joint-diagonalisation workspace; it is allocated by the first multi-block
+// call (depth < 0: keep the wanted depth, just make sure the workspace exists), so per-block users never pay for it.
+int ensure_depth(Handle& h, int depth) {
+  if (depth >= 0) h.depth = (depth >= 2 && h.nz > 0) ? 2 : 1;
+  else if (h.depth == 2 && h.jd2.n == 0) APV_TRY(jdiag_alloc(h.jd2, h.D.n, h.D.V, h.nz, h.cfg.eig_mode));
+  return OK;
 }
 
 // after a multi-block call: the filters / outputs of the last block back into the handle's own buffers, so that
 // apv_get and the next per-block call see the usual layout
 int leave_multiblock(Handle& h) {
   const Dims& D = h.D;
+  if (h.depth == 2 && pipelined(h)) {          // the second back-half stream joins the main stream
+    APV_CUDA_TRY(cudaEventRecord(h.ev_join, h.st_back2));
+    APV_CUDA_TRY(cudaStreamWaitEvent(h.st, h.ev_join, 0));
+    if (h.last_ws == 1) std::swap(h.jd, h.jd2);   // h.jd = the workspace of the most recent block (apv_sweep, timers)
+    h.last_ws = 0;
+  }
   if (h.W != h.home_W)
     APV_CUDA_TRY(cudaMemcpyAsync(h.home_W, h.W, 2 * (size_t)D.V * D.n * sizeof(double), cudaMemcpyDeviceToDevice, h.st));
   if (h.d_out != h.home_out)
@@ -393,10 +427,13 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
     CUB(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
     CUB(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));
     CUB(cudaStreamCreateWithPriority(&h->st_copy, cudaStreamNonBlocking, hi));
+    CUB(cudaStreamCreateWithPriority(&h->st_back2, cudaStreamNonBlocking, hi));
   }
   for (auto& e : h->ev) CUB(cudaEventCreate(&e));
   for (auto& e : h->ev_ready) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev_free) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUB(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+  CUB(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   for (auto& e : h->ev_rend) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev_d2h) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   {
@@ -426,7 +463,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
   TRYB(dalloc(&h->G, 2 * V * L * Nb));
   TRYB(dalloc(&h->Gt, 2 * Nb));
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < Handle::NSLOT; ++s) {
     TRYB(dalloc(&h->Rslot[s], 4 * n * (size_t)D.ldn));
     TRYB(dalloc(&h->rvslot[s], 2 * n));
     TRYB(dalloc(&h->xwslot[s], 2 * Nb));
@@ -445,6 +482,12 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   if (D.runB) h->zones[h->nz++] = 1;
   if (h->nz == 1) h->zones[1] = h->zones[0];
   if (h->nz > 0) TRYB(jdiag_alloc(h->jd, D.n, D.V, h->nz, cfg->eig_mode));
+  {
+    // two joint diagonalisations in flight in multi-block calls (measured at cfg-3: 110.5 -> 99.2 ms per block, at
+    // cfg-2: 12.4 -> 8.5 ms); APV_DEPTH=1 switches it off
+    const char* de = getenv("APV_DEPTH");
+    TRYB(ensure_depth(*h, de ? atoi(de) : 2));
+  }
   if (fft_plan(D.Nb, h->rad, &h->nrad) != OK) return bail(fail(EINVAL_, "cannot factor block size %d", D.Nb));
 
   // host-side constant tables
@@ -510,17 +553,21 @@ void apv_destroy(apv_handle* h) {
   range_free(*h);
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
                 h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->Rslot[0], h->Rslot[1],
-                h->rvslot[0], h->rvslot[1], h->xwslot[0], h->xwslot[1], h->regv, h->lam, h->U, h->home_W, h->d_in,
-                h->home_out, h->home_out_t, h->ring};
+                h->Rslot[2], h->rvslot[0], h->rvslot[1], h->rvslot[2], h->xwslot[0], h->xwslot[1], h->xwslot[2], h->regv,
+                h->lam, h->U, h->home_W, h->d_in, h->home_out, h->home_out_t, h->ring};
   for (void* p : ps)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ring_pin) cudaFreeHost(h->ring_pin);
   if (h->ring_info) cudaFreeHost(h->ring_info);
   jdiag_free(h->jd);
+  jdiag_free(h->jd2);
   for (cudaEvent_t* arr : {h->ev_ready, h->ev_free})
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < Handle::NSLOT; ++i)
       if (arr[i]) cudaEventDestroy(arr[i]);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->st_back2) { cudaStreamSynchronize(h->st_back2); cudaStreamDestroy(h->st_back2); }
   for (cudaEvent_t* arr : {h->ev_rend, h->ev_d2h})
     for (int i = 0; i < 4; ++i)
       if (arr[i]) cudaEventDestroy(arr[i]);
@@ -563,6 +610,7 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   const size_t sd = ring_slot_doubles(D);
   const int cap = sd * sizeof(double) > ((size_t)256 << 20) ? 2 : 3;
   APV_TRY(ensure_ring(*h, cap));
+  APV_TRY(ensure_depth(*h, -1));
   double* d_sig = nullptr;       // [2][nblocks][H]
   const size_t sig = (size_t)nblocks * D.H;
   APV_CUDA_TRY(cudaMalloc((void**)&d_sig, 2 * sig * sizeof(double)));
@@ -600,12 +648,14 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   for (long b = 0; b < nblocks && rc == OK; ++b) {
     const int rs = (int)(b % cap);
     double* slot = h->ring + (size_t)rs * sd;
-    if (b >= cap) cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
+    if (b >= cap) {               // the slot's previous contents have left for the host (either back-half stream may render next)
+      cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
+      cu(cudaStreamWaitEvent(h->st_back2, h->ev_d2h[rs], 0), "wait ring slot");
+    }
     BlockSink sink{slot, slot + 2 * per, slot + 2 * per + 2 * (size_t)D.H,
                    reinterpret_cast<int*>(slot + 2 * per + 2 * (size_t)D.H + perw)};
-    if (rc == OK) rc = enqueue_back(*h, b, sink);
+    if (rc == OK) rc = enqueue_back(*h, b, sink, h->ev_rend[rs]);
     if (rc == OK && b + 1 < nblocks) rc = enqueue_front(*h, b + 1, sig_ptr(0, b + 1), sig_ptr(1, b + 1), false);
-    cu(cudaEventRecord(h->ev_rend[rs], h->st), "record");
     cu(cudaStreamWaitEvent(h->st_copy, h->ev_rend[rs], 0), "wait render");
     cu(cudaMemcpyAsync(h->ring_pin + (size_t)rs * sd, slot, sd * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy), "D2H");
     cu(cudaEventRecord(h->ev_d2h[rs], h->st_copy), "record");
@@ -615,6 +665,7 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   const int rc2 = leave_multiblock(*h);
   cudaStreamSynchronize(h->st_front);
   cudaStreamSynchronize(h->st_copy);
+  cudaStreamSynchronize(h->st_back2);
   cudaStreamSynchronize(h->st);
   cudaFree(d_sig);
   return rc != OK ? rc : rc2;
@@ -708,6 +759,13 @@ int apv_set_pipeline(apv_handle* h, int on) {
   if (!h) return fail(EINVAL_, "null argument");
   h->pipeline = on < 0 ? 0 : (on > 2 ? 2 : on);
   return OK;
+}
+
+int apv_set_depth(apv_handle* h, int depth) {
+  if (!h) return fail(EINVAL_, "null argument");
+  DevGuard dg(h->device);
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st));
+  return ensure_depth(*h, depth);
 }
 
 int apv_set_reg_mode(apv_handle* h, int relative) {
@@ -841,6 +899,7 @@ int apv_synchronize(apv_handle* h) {
   DevGuard dg(h->device);
   APV_CUDA_TRY(cudaStreamSynchronize(h->st_front));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st_copy));
+  APV_CUDA_TRY(cudaStreamSynchronize(h->st_back2));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   return OK;
 }

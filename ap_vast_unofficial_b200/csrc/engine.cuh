@@ -112,11 +112,17 @@ struct Handle {
   // results.  R, rvec and xw exist in two slots so that the statistics of block t+1 can be formed while block t is
   // still being diagonalised and rendered (apv_process_blocks / apv_range_run); R, rvec, xw point at the slot of the
   // block whose S5-S7 ran last.
-  double* Rslot[2] = {nullptr, nullptr};     // [4][n][ldn]
-  double* rvslot[2] = {nullptr, nullptr};    // [2][n]
-  double* xwslot[2] = {nullptr, nullptr};    // [2][Nb]  window * input block (what S7 filters, apvast.py:430-431)
-  cudaEvent_t ev_ready[2] = {};              // front of the slot finished (statistics ready)
-  cudaEvent_t ev_free[2] = {};               // back of the slot finished (slot may be overwritten)
+  static constexpr int NSLOT = 3;
+  double* Rslot[NSLOT] = {};                 // [4][n][ldn]
+  double* rvslot[NSLOT] = {};                // [2][n]
+  double* xwslot[NSLOT] = {};                // [2][Nb]  window * input block (what S7 filters, apvast.py:430-431)
+  cudaEvent_t ev_ready[NSLOT] = {};          // front of the slot finished (statistics ready)
+  cudaEvent_t ev_free[NSLOT] = {};           // back of the slot finished (slot may be overwritten)
+  cudaEvent_t ev_order = nullptr;            // S6 + S7 of the previous block finished (the overlap buffers G are sequential state)
+  cudaEvent_t ev_join = nullptr;             // hand-over between the main stream and the others at the ends of a call
+  cudaStream_t st_back2 = nullptr;           // second back-half stream (depth 2)
+  int depth = 1;                             // back halves (S5-S7) in flight in a multi-block call: 1 or 2
+  int last_ws = 0;                           // joint-diagonalisation workspace the last back half used
   double* R = nullptr;       // [4][n][ldn]
   double* rvec = nullptr;    // [2][n]
   double* xw = nullptr;      // [2][Nb]
@@ -158,6 +164,7 @@ struct Handle {
   void* comm = nullptr;      // ncclComm_t
   int comm_rank = 0, comm_size = 1;
   JdiagWs jd;
+  JdiagWs jd2;               // second workspace: two joint diagonalisations in flight (depth 2; allocated on demand)
   int nz = 0;
   int zones[2] = {0, 1};
   float stage_ms[7] = {};
@@ -183,7 +190,7 @@ int stage_spectral_norms(Handle& h);                                          //
 int fft_plan(int n, int* rad, int* nrad);
 // engine.cu internals used by comm.cu
 int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only);
-int run_back(Handle& h);
+int run_back(Handle& h, cudaEvent_t order = nullptr);
 int fail(int code, const char* fmt, ...);
 struct DevGuard {   // entry points run on the handle's device whatever the caller's current device is
   int prev = -1, dev = -1;
@@ -203,7 +210,8 @@ struct BlockSink {   // device destinations of one block's results (nullptr = th
 };
 bool pipelined(const Handle& h);
 int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only);
-int enqueue_back(Handle& h, long b, const BlockSink& sink);
+int enqueue_back(Handle& h, long b, const BlockSink& sink, cudaEvent_t done = nullptr);
+int ensure_depth(Handle& h, int depth);
 int leave_multiblock(Handle& h);
 int status_from_info(const Handle& h, const int* info, long block);
 int range_alloc(Handle& h, int max_owned, int total_on_root);

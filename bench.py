@@ -521,8 +521,8 @@ def run_ours(args, rank, world, local_rank):
                 "api": "apv_range_run + apv_range_exchange_halo + apv_range_gather (sharded.RangeRunner), host buffers"},
         "gpu_launches": launches_block * K + 4 * n_halo + 3,
         "timed_region": {"per_rank": f"{rr.halo} halo blocks (S1-S3; rank 0 has none) + {K} owned blocks "
-                                     f"(pipelined: S1-S4 of block t+1 overlap S5-S7 of block t) + overlap-add tail "
-                                     f"exchange + gather to rank 0",
+                                     f"(pipelined: S1-S4 of later blocks and the joint diagonalisations of two consecutive "
+                                     f"blocks overlap) + overlap-add tail exchange + gather to rank 0",
                          "pipeline": not args.no_pipeline, "launches_per_block": launches_block},
         "collective": {"halo": {"op": "ncclSend/ncclRecv (device to device, issued by the library on the engine's stream)",
                                 "messages": world - 1, "bytes_per_message": rr.bytes_halo},

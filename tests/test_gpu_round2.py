@@ -45,9 +45,10 @@ def test_process_blocks_pipelined_is_bit_identical_to_the_per_hop_loop(shape):
         oA, oB, oAt, oBt = e1.process_input_buffers(sA[t * H:(t + 1) * H], sB[t * H:(t + 1) * H])
         ref_A.append(np.stack(oA)); ref_B.append(np.stack(oB)); ref_At.append(oAt[0].copy())
         ref_w.append(np.stack([e1.w_A[:, :, 0], e1.w_B[:, :, 0]]))
-    for pipe in (True, 1, False):
+    for pipe, depth in ((True, 2), (True, 1), (1, 2), (1, 1), (False, 1)):
         np.random.seed(0); e2 = _engine()(rir_A=rA, rir_B=rB, eig_mode=eig_mode, **cfg)
         e2.set_pipeline(pipe)
+        e2.set_depth(depth)          # joint diagonalisations of two consecutive blocks side by side, or one at a time
         # two calls: the second one starts from the state the first one left (the streams must hand over correctly)
         k = nblk // 2
         a1 = e2.process_blocks(sA[:k * H], sB[:k * H], want_filters=True)
@@ -55,10 +56,10 @@ def test_process_blocks_pipelined_is_bit_identical_to_the_per_hop_loop(shape):
         oA = np.concatenate([a1[0], a2[0]]); oB = np.concatenate([a1[1], a2[1]])
         oAt = np.concatenate([a1[2], a2[2]]); w = np.concatenate([a1[4], a2[4]])
         for t in range(nblk):
-            assert np.array_equal(oA[t], ref_A[t]), (pipe, t)
-            assert np.array_equal(oB[t], ref_B[t]), (pipe, t)
-            assert np.array_equal(oAt[t], ref_At[t]), (pipe, t)
-            assert np.array_equal(w[t], ref_w[t]), (pipe, t)
+            assert np.array_equal(oA[t], ref_A[t]), (pipe, depth, t)
+            assert np.array_equal(oB[t], ref_B[t]), (pipe, depth, t)
+            assert np.array_equal(oAt[t], ref_At[t]), (pipe, depth, t)
+            assert np.array_equal(w[t], ref_w[t]), (pipe, depth, t)
         # the handle is left in the per-block layout: attributes and the next per-hop call see the last block
         assert np.array_equal(e2.w_A[:, :, 0], ref_w[-1][0])
         assert np.array_equal(e2.R_A_to_A, e1.R_A_to_A)
