@@ -235,26 +235,26 @@ bool pipelined(const Handle& h) {
 // leave most SMs idle, and the statistics fill them.  The caller enqueues back(b) BEFORE front(b + 1) so that the
 // event is recorded when the wait is enqueued.  `b` counts from 0 inside the call.
 int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, bool state_only) {
-  const int slot = (int)(b % Handle::NSLOT);
+  const int slot = (int)(b % h.nslot);
   const bool pipe = pipelined(h) && !state_only;
-  const bool two = pipe && h.depth == 2;
+  const bool two = pipe && h.depth >= 2;
   cudaStream_t main_st = h.st;
   h.launches_front = 0;
   const int saved = h.launches;
   h.launches = 0;
   use_slot(h, slot);
   if (pipe) {
-    if (b >= Handle::NSLOT) {
-      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[slot], 0));     // back half of block b - 3 released the slot
+    if (b >= h.nslot) {
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[slot], 0));     // back half of block b - nslot released the slot
     } else if (b == 0) {
       APV_CUDA_TRY(cudaEventRecord(h.ev_join, main_st));                     // state written by earlier calls
       APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_join, 0));
-      if (two) APV_CUDA_TRY(cudaStreamWaitEvent(h.st_back2, h.ev_join, 0));
+      for (int k = 0; two && k < h.depth - 1; ++k) APV_CUDA_TRY(cudaStreamWaitEvent(h.st_backx[k], h.ev_join, 0));
     }
     if (b >= 1 && h.pipeline == 2 && !two && h.nz > 0 && h.jd.last_two_stage)
       APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.jd.ev2[0], 0));         // block b - 1 has reached its bulge chasing
     if (b >= 2 && !two)
-      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[(b - 2) % Handle::NSLOT], 0));   // depth 1: at most one block ahead
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st_front, h.ev_free[(b - 2) % h.nslot], 0));   // depth 1: at most one block ahead
     h.st = h.st_front;
   }
   if (h.dbg_ev && !state_only && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 0], h.st);
@@ -273,19 +273,19 @@ int enqueue_front(Handle& h, long b, const double* d_inA, const double* d_inB, b
 // consecutive blocks alternate between two streams and two joint-diagonalisation workspaces, so two S5 run side by
 // side; S6 / S7 stay in block order (ev_order).
 int enqueue_back(Handle& h, long b, const BlockSink& sink, cudaEvent_t done) {
-  const int slot = (int)(b % Handle::NSLOT);
+  const int slot = (int)(b % h.nslot);
   const bool pipe = pipelined(h);
-  const bool two = pipe && h.depth == 2;
-  const int which = two ? (int)(b & 1) : 0;
+  const bool two = pipe && h.depth >= 2;
+  const int which = two ? (int)(b % h.depth) : 0;
   cudaStream_t main_st = h.st;
-  cudaStream_t sb = which ? h.st_back2 : main_st;
+  cudaStream_t sb = which ? h.st_backx[which - 1] : main_st;
   use_slot(h, slot);
   h.launches = h.launches_front;
   if (pipe) APV_CUDA_TRY(cudaStreamWaitEvent(sb, h.ev_ready[slot], 0));
   h.W = sink.W ? sink.W : h.home_W;
   h.d_out = sink.out ? sink.out : h.home_out;
   h.d_out_t = sink.out_t ? sink.out_t : h.home_out_t;
-  if (which) std::swap(h.jd, h.jd2);
+  if (which) std::swap(h.jd, h.jdx[which - 1]);
   h.st = sb;
   if (h.dbg_ev && b < h.dbg_cap) cudaEventRecord(h.dbg_ev[b * 4 + 2], sb);
   int rc = run_back(h, (two && b >= 1) ? h.ev_order : nullptr);
@@ -297,16 +297,33 @@ int enqueue_back(Handle& h, long b, const BlockSink& sink, cudaEvent_t done) {
   if (rc == OK && pipe) rc = cudaEventRecord(h.ev_free[slot], sb) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
   if (rc == OK && done) rc = cudaEventRecord(done, sb) == cudaSuccess ? OK : fail(ECUDA, "event record failed");
   h.st = main_st;
-  if (which) std::swap(h.jd, h.jd2);
+  if (which) std::swap(h.jd, h.jdx[which - 1]);
   h.last_ws = which;
   return rc;
 }
 
-// Two back halves in flight need a second joint-diagonalisation workspace; it is allocated by the first multi-block
-// call (depth < 0: keep the wanted depth, just make sure the workspace exists), so per-block users never pay for it.
+// D back halves in flight need D joint-diagonalisation workspaces and D + 1 statistics slots; the extra ones are
+// allocated by the first multi-block call (depth < 0: keep the wanted depth, just make sure they exist), so per-block
+// users never pay for them.
 int ensure_depth(Handle& h, int depth) {
-  if (depth >= 0) h.depth = (depth >= 2 && h.nz > 0) ? 2 : 1;
-  else if (h.depth == 2 && h.jd2.n == 0) APV_TRY(jdiag_alloc(h.jd2, h.D.n, h.D.V, h.nz, h.cfg.eig_mode));
+  if (depth >= 0) {
+    h.depth = h.nz > 0 ? std::max(1, std::min(depth, (int)Handle::MAXDEPTH)) : 1;
+    return OK;
+  }
+  const Dims& D = h.D;
+  for (int k = 0; k < h.depth - 1; ++k)
+    if (h.jdx[k].n == 0) APV_TRY(jdiag_alloc(h.jdx[k], D.n, D.V, h.nz, h.cfg.eig_mode));
+  const int want = std::max(2, h.depth + 1);
+  for (int s = 0; s < want; ++s) {
+    if (h.Rslot[s]) continue;
+    APV_CUDA_TRY(cudaMalloc((void**)&h.Rslot[s], 4 * (size_t)D.n * D.ldn * sizeof(double)));
+    APV_CUDA_TRY(cudaMalloc((void**)&h.rvslot[s], 2 * (size_t)D.n * sizeof(double)));
+    APV_CUDA_TRY(cudaMalloc((void**)&h.xwslot[s], 2 * (size_t)D.Nb * sizeof(double)));
+    APV_CUDA_TRY(cudaMemsetAsync(h.Rslot[s], 0, 4 * (size_t)D.n * D.ldn * sizeof(double), h.st));
+    APV_CUDA_TRY(cudaMemsetAsync(h.rvslot[s], 0, 2 * (size_t)D.n * sizeof(double), h.st));
+    APV_CUDA_TRY(cudaMemsetAsync(h.xwslot[s], 0, 2 * (size_t)D.Nb * sizeof(double), h.st));
+  }
+  h.nslot = want;
   return OK;
 }
 
@@ -314,10 +331,12 @@ int ensure_depth(Handle& h, int depth) {
 // apv_get and the next per-block call see the usual layout
 int leave_multiblock(Handle& h) {
   const Dims& D = h.D;
-  if (h.depth == 2 && pipelined(h)) {          // the second back-half stream joins the main stream
-    APV_CUDA_TRY(cudaEventRecord(h.ev_join, h.st_back2));
-    APV_CUDA_TRY(cudaStreamWaitEvent(h.st, h.ev_join, 0));
-    if (h.last_ws == 1) std::swap(h.jd, h.jd2);   // h.jd = the workspace of the most recent block (apv_sweep, timers)
+  if (h.depth >= 2 && pipelined(h)) {          // the other back-half streams join the main stream
+    for (int k = 0; k < h.depth - 1; ++k) {
+      APV_CUDA_TRY(cudaEventRecord(h.ev_join, h.st_backx[k]));
+      APV_CUDA_TRY(cudaStreamWaitEvent(h.st, h.ev_join, 0));
+    }
+    if (h.last_ws > 0) std::swap(h.jd, h.jdx[h.last_ws - 1]);   // h.jd = the workspace of the most recent block (apv_sweep, timers)
     h.last_ws = 0;
   }
   if (h.W != h.home_W)
@@ -427,7 +446,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
     CUB(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
     CUB(cudaStreamCreateWithPriority(&h->st_front, cudaStreamNonBlocking, lo));
     CUB(cudaStreamCreateWithPriority(&h->st_copy, cudaStreamNonBlocking, hi));
-    CUB(cudaStreamCreateWithPriority(&h->st_back2, cudaStreamNonBlocking, hi));
+    for (auto& sx : h->st_backx) CUB(cudaStreamCreateWithPriority(&sx, cudaStreamNonBlocking, hi));
   }
   for (auto& e : h->ev) CUB(cudaEventCreate(&e));
   for (auto& e : h->ev_ready) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -463,7 +482,7 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
   TRYB(dalloc(&h->G, 2 * V * L * Nb));
   TRYB(dalloc(&h->Gt, 2 * Nb));
-  for (int s = 0; s < Handle::NSLOT; ++s) {
+  for (int s = 0; s < 2; ++s) {              // (further slots: ensure_depth, on the first multi-block call)
     TRYB(dalloc(&h->Rslot[s], 4 * n * (size_t)D.ldn));
     TRYB(dalloc(&h->rvslot[s], 2 * n));
     TRYB(dalloc(&h->xwslot[s], 2 * Nb));
@@ -483,10 +502,10 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   if (h->nz == 1) h->zones[1] = h->zones[0];
   if (h->nz > 0) TRYB(jdiag_alloc(h->jd, D.n, D.V, h->nz, cfg->eig_mode));
   {
-    // two joint diagonalisations in flight in multi-block calls (measured at cfg-3: 110.5 -> 99.2 ms per block, at
-    // cfg-2: 12.4 -> 8.5 ms); APV_DEPTH=1 switches it off
+    // joint diagonalisations in flight in multi-block calls: 2 where one of them nearly fills the chip (measured at
+    // cfg-3: 110.5 -> 99.2 ms per block), 4 below n = 2048 where S5 is latency-bound throughout; APV_DEPTH overrides
     const char* de = getenv("APV_DEPTH");
-    TRYB(ensure_depth(*h, de ? atoi(de) : 2));
+    TRYB(ensure_depth(*h, de ? atoi(de) : (D.n < 2048 ? 4 : 2)));
   }
   if (fft_plan(D.Nb, h->rad, &h->nrad) != OK) return bail(fail(EINVAL_, "cannot factor block size %d", D.Nb));
 
@@ -552,22 +571,25 @@ void apv_destroy(apv_handle* h) {
   if (h->st_copy) cudaStreamSynchronize(h->st_copy);
   range_free(*h);
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
-                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->Rslot[0], h->Rslot[1],
-                h->Rslot[2], h->rvslot[0], h->rvslot[1], h->rvslot[2], h->xwslot[0], h->xwslot[1], h->xwslot[2], h->regv,
+                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->regv,
                 h->lam, h->U, h->home_W, h->d_in, h->home_out, h->home_out_t, h->ring};
   for (void* p : ps)
     if (p) cudaFree(p);
+  for (int s = 0; s < Handle::NSLOT; ++s)
+    for (void* p : {(void*)h->Rslot[s], (void*)h->rvslot[s], (void*)h->xwslot[s]})
+      if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ring_pin) cudaFreeHost(h->ring_pin);
   if (h->ring_info) cudaFreeHost(h->ring_info);
   jdiag_free(h->jd);
-  jdiag_free(h->jd2);
+  for (auto& w : h->jdx) jdiag_free(w);
   for (cudaEvent_t* arr : {h->ev_ready, h->ev_free})
     for (int i = 0; i < Handle::NSLOT; ++i)
       if (arr[i]) cudaEventDestroy(arr[i]);
   if (h->ev_order) cudaEventDestroy(h->ev_order);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->st_back2) { cudaStreamSynchronize(h->st_back2); cudaStreamDestroy(h->st_back2); }
+  for (auto& sx : h->st_backx)
+    if (sx) { cudaStreamSynchronize(sx); cudaStreamDestroy(sx); }
   for (cudaEvent_t* arr : {h->ev_rend, h->ev_d2h})
     for (int i = 0; i < 4; ++i)
       if (arr[i]) cudaEventDestroy(arr[i]);
@@ -608,9 +630,10 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   const Dims& D = h->D;
   const size_t per = (size_t)D.V * D.H * D.L, pert = (size_t)D.H * D.L, perw = 2 * (size_t)D.V * D.n;
   const size_t sd = ring_slot_doubles(D);
+  APV_TRY(ensure_depth(*h, -1));
+  // (ring slots are written by S6 / S7 only, which stay in block order whatever the depth: three slots are enough)
   const int cap = sd * sizeof(double) > ((size_t)256 << 20) ? 2 : 3;
   APV_TRY(ensure_ring(*h, cap));
-  APV_TRY(ensure_depth(*h, -1));
   double* d_sig = nullptr;       // [2][nblocks][H]
   const size_t sig = (size_t)nblocks * D.H;
   APV_CUDA_TRY(cudaMalloc((void**)&d_sig, 2 * sig * sizeof(double)));
@@ -650,7 +673,7 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
     double* slot = h->ring + (size_t)rs * sd;
     if (b >= cap) {               // the slot's previous contents have left for the host (either back-half stream may render next)
       cu(cudaStreamWaitEvent(h->st, h->ev_d2h[rs], 0), "wait ring slot");
-      cu(cudaStreamWaitEvent(h->st_back2, h->ev_d2h[rs], 0), "wait ring slot");
+      for (auto& sx : h->st_backx) cu(cudaStreamWaitEvent(sx, h->ev_d2h[rs], 0), "wait ring slot");
     }
     BlockSink sink{slot, slot + 2 * per, slot + 2 * per + 2 * (size_t)D.H,
                    reinterpret_cast<int*>(slot + 2 * per + 2 * (size_t)D.H + perw)};
@@ -665,7 +688,7 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   const int rc2 = leave_multiblock(*h);
   cudaStreamSynchronize(h->st_front);
   cudaStreamSynchronize(h->st_copy);
-  cudaStreamSynchronize(h->st_back2);
+  for (auto& sx : h->st_backx) cudaStreamSynchronize(sx);
   cudaStreamSynchronize(h->st);
   cudaFree(d_sig);
   return rc != OK ? rc : rc2;
@@ -899,7 +922,7 @@ int apv_synchronize(apv_handle* h) {
   DevGuard dg(h->device);
   APV_CUDA_TRY(cudaStreamSynchronize(h->st_front));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st_copy));
-  APV_CUDA_TRY(cudaStreamSynchronize(h->st_back2));
+  for (auto& sx : h->st_backx) APV_CUDA_TRY(cudaStreamSynchronize(sx));
   APV_CUDA_TRY(cudaStreamSynchronize(h->st));
   return OK;
 }

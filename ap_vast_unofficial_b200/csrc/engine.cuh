@@ -112,7 +112,9 @@ struct Handle {
   // results.  R, rvec and xw exist in two slots so that the statistics of block t+1 can be formed while block t is
   // still being diagonalised and rendered (apv_process_blocks / apv_range_run); R, rvec, xw point at the slot of the
   // block whose S5-S7 ran last.
-  static constexpr int NSLOT = 3;
+  static constexpr int MAXDEPTH = 4;        // back halves in flight
+  static constexpr int NSLOT = MAXDEPTH + 1; // statistics slots: every back half in flight holds one, a front half fills one
+  int nslot = 2;                             // slots in use = depth + 1 (allocated on demand beyond the first two)
   double* Rslot[NSLOT] = {};                 // [4][n][ldn]
   double* rvslot[NSLOT] = {};                // [2][n]
   double* xwslot[NSLOT] = {};                // [2][Nb]  window * input block (what S7 filters, apvast.py:430-431)
@@ -120,8 +122,8 @@ struct Handle {
   cudaEvent_t ev_free[NSLOT] = {};           // back of the slot finished (slot may be overwritten)
   cudaEvent_t ev_order = nullptr;            // S6 + S7 of the previous block finished (the overlap buffers G are sequential state)
   cudaEvent_t ev_join = nullptr;             // hand-over between the main stream and the others at the ends of a call
-  cudaStream_t st_back2 = nullptr;           // second back-half stream (depth 2)
-  int depth = 1;                             // back halves (S5-S7) in flight in a multi-block call: 1 or 2
+  cudaStream_t st_backx[MAXDEPTH - 1] = {};  // further back-half streams (depth 2..4); the first back-half stream is `st`
+  int depth = 1;                             // back halves (S5-S7) in flight in a multi-block call: 1..4
   int last_ws = 0;                           // joint-diagonalisation workspace the last back half used
   double* R = nullptr;       // [4][n][ldn]
   double* rvec = nullptr;    // [2][n]
@@ -164,7 +166,7 @@ struct Handle {
   void* comm = nullptr;      // ncclComm_t
   int comm_rank = 0, comm_size = 1;
   JdiagWs jd;
-  JdiagWs jd2;               // second workspace: two joint diagonalisations in flight (depth 2; allocated on demand)
+  JdiagWs jdx[3];            // further workspaces: up to four joint diagonalisations in flight (allocated on demand)
   int nz = 0;
   int zones[2] = {0, 1};
   float stage_ms[7] = {};

@@ -149,9 +149,10 @@ int apv_advance_state(apv_handle* h, const double* in_A, const double* in_B);
  * with S5-S7 of block t; 2 (default, also env APV_PIPELINE): they start when block t reaches its bulge chasing, the
  * point from which S5 leaves most SMs idle.  Results are bit-identical in all three. */
 int apv_set_pipeline(apv_handle* h, int on);
-/* Back halves (S5-S7) in flight in a multi-block call: 1, or 2 = the joint diagonalisations of consecutive blocks run
- * side by side on two streams and two workspaces while S6/S7 stay in block order (default; the second workspace is
- * allocated by the first multi-block call; env APV_DEPTH overrides).  Results are bit-identical. */
+/* Back halves (S5-S7) in flight in a multi-block call, 1..4: the joint diagonalisations of consecutive blocks run side
+ * by side on their own streams and workspaces while S6/S7 stay in block order.  Default 2 (4 for n < 2048, where S5 is
+ * latency-bound throughout); the extra workspaces are allocated by the first multi-block call; env APV_DEPTH
+ * overrides.  Results are bit-identical. */
 int apv_set_depth(apv_handle* h, int depth);
 /* Diagnostic timeline of a multi-block call: arm with ms == NULL, run, read back (nblocks, 4) milliseconds
  * (front start, front end, back start, back end per block, relative to the first event). */

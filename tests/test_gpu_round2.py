@@ -45,7 +45,7 @@ def test_process_blocks_pipelined_is_bit_identical_to_the_per_hop_loop(shape):
         oA, oB, oAt, oBt = e1.process_input_buffers(sA[t * H:(t + 1) * H], sB[t * H:(t + 1) * H])
         ref_A.append(np.stack(oA)); ref_B.append(np.stack(oB)); ref_At.append(oAt[0].copy())
         ref_w.append(np.stack([e1.w_A[:, :, 0], e1.w_B[:, :, 0]]))
-    for pipe, depth in ((True, 2), (True, 1), (1, 2), (1, 1), (False, 1)):
+    for pipe, depth in ((True, 4), (True, 3), (True, 2), (True, 1), (1, 2), (1, 1), (False, 1)):
         np.random.seed(0); e2 = _engine()(rir_A=rA, rir_B=rB, eig_mode=eig_mode, **cfg)
         e2.set_pipeline(pipe)
         e2.set_depth(depth)          # joint diagonalisations of two consecutive blocks side by side, or one at a time
