@@ -591,7 +591,7 @@ void apv_destroy(apv_handle* h) {
   for (auto& sx : h->st_backx)
     if (sx) { cudaStreamSynchronize(sx); cudaStreamDestroy(sx); }
   for (cudaEvent_t* arr : {h->ev_rend, h->ev_d2h})
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
       if (arr[i]) cudaEventDestroy(arr[i]);
   if (h->st_front) cudaStreamDestroy(h->st_front);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
@@ -631,8 +631,10 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
   const size_t per = (size_t)D.V * D.H * D.L, pert = (size_t)D.H * D.L, perw = 2 * (size_t)D.V * D.n;
   const size_t sd = ring_slot_doubles(D);
   APV_TRY(ensure_depth(*h, -1));
-  // (ring slots are written by S6 / S7 only, which stay in block order whatever the depth: three slots are enough)
-  const int cap = sd * sizeof(double) > ((size_t)256 << 20) ? 2 : 3;
+  // the host hands blocks to the caller `lag` blocks behind its own enqueueing, so that `depth` back halves can be in
+  // flight on the device; the rings hold the blocks in between
+  const int lag = sd * sizeof(double) > ((size_t)256 << 20) ? 1 : std::max(1, std::min(h->depth, 6));
+  const int cap = lag + 1 + (lag > 1 ? 1 : (sd * sizeof(double) > ((size_t)256 << 20) ? 0 : 1));
   APV_TRY(ensure_ring(*h, cap));
   double* d_sig = nullptr;       // [2][nblocks][H]
   const size_t sig = (size_t)nblocks * D.H;
@@ -682,9 +684,9 @@ int apv_process_blocks(apv_handle* h, int nblocks, const double* in_A, const dou
     cu(cudaStreamWaitEvent(h->st_copy, h->ev_rend[rs], 0), "wait render");
     cu(cudaMemcpyAsync(h->ring_pin + (size_t)rs * sd, slot, sd * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy), "D2H");
     cu(cudaEventRecord(h->ev_d2h[rs], h->st_copy), "record");
-    if (b >= 1 && rc == OK) retire(b - 1);
+    if (b >= lag && rc == OK) retire(b - lag);
   }
-  if (rc == OK) retire(nblocks - 1);
+  for (long b = std::max(0L, (long)nblocks - lag); b < nblocks && rc == OK; ++b) retire(b);
   const int rc2 = leave_multiblock(*h);
   cudaStreamSynchronize(h->st_front);
   cudaStreamSynchronize(h->st_copy);

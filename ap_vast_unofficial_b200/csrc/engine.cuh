@@ -147,8 +147,8 @@ struct Handle {
   double* ring_pin = nullptr;
   int ring_pin_cap = 0;
   int* ring_info = nullptr;  // pinned [ring_pin_cap][8]
-  cudaEvent_t ev_rend[4] = {};   // block rendered into its ring slot
-  cudaEvent_t ev_d2h[4] = {};    // ring slot copied to the pinned ring
+  cudaEvent_t ev_rend[8] = {};   // block rendered into its ring slot
+  cudaEvent_t ev_d2h[8] = {};    // ring slot copied to the pinned ring
   int pipeline = 1;          // 0: S1-S7 of consecutive blocks strictly in order on one stream
   // block-range sharding (comm.cu)
   double* rg_out = nullptr;  // [rg_cap][2][V][H][L] rendered outputs of the owned blocks
