@@ -578,6 +578,8 @@ void apv_destroy(apv_handle* h) {
   for (int s = 0; s < Handle::NSLOT; ++s)
     for (void* p : {(void*)h->Rslot[s], (void*)h->rvslot[s], (void*)h->xwslot[s]})
       if (p) cudaFree(p);
+  if (h->sw_mu) cudaFree(h->sw_mu);
+  if (h->sw_m) cudaFree(h->sw_m);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ring_pin) cudaFreeHost(h->ring_pin);
   if (h->ring_info) cudaFreeHost(h->ring_info);
@@ -877,13 +879,29 @@ int apv_sweep(apv_handle* h, int n_mu, const double* mu, double* w_out) {
 /* Sweep without leaving the device: filters for every mu into a caller-owned DEVICE buffer (n_mu, 2, V, n) (may be
  * NULL) and the eigen-basis figures of merit (n_mu, 2, V, 3) = {dark energy, bright energy, w . r_B} per rank to the
  * host (may be NULL).  The full-rank sweep of BASELINE cfg-4 is 2 GB of filters per block: they stay in HBM. */
+static int sweep_scratch(Handle& h, size_t n_mu, size_t n_metrics) {
+  if (n_mu > h.sw_mu_cap) {
+    if (h.sw_mu) cudaFree(h.sw_mu);
+    h.sw_mu = nullptr; h.sw_mu_cap = 0;
+    APV_CUDA_TRY(cudaMalloc((void**)&h.sw_mu, std::max<size_t>(n_mu, 64) * sizeof(double)));
+    h.sw_mu_cap = std::max<size_t>(n_mu, 64);
+  }
+  if (n_metrics > h.sw_m_cap) {
+    if (h.sw_m) cudaFree(h.sw_m);
+    h.sw_m = nullptr; h.sw_m_cap = 0;
+    APV_CUDA_TRY(cudaMalloc((void**)&h.sw_m, n_metrics * sizeof(double)));
+    h.sw_m_cap = n_metrics;
+  }
+  return OK;
+}
+
 int apv_sweep_device(apv_handle* h, int n_mu, const double* mu, void* d_w_out, double* metrics_out) {
   if (!h || !mu || n_mu < 1) return fail(EINVAL_, "bad argument");
   DevGuard dg(h->device);
   const Dims& D = h->D;
-  double *d_mu = nullptr, *d_m = nullptr;
   const size_t mc = (size_t)n_mu * 2 * D.V * 3;
-  APV_CUDA_TRY(cudaMalloc((void**)&d_mu, n_mu * sizeof(double)));
+  APV_TRY(sweep_scratch(*h, (size_t)n_mu, metrics_out ? mc : 0));
+  double* d_mu = h->sw_mu;
   int rc = OK;
   if (cudaMemcpyAsync(d_mu, mu, n_mu * sizeof(double), cudaMemcpyHostToDevice, h->st) != cudaSuccess) rc = fail(ECUDA, "mu copy failed");
   if (rc == OK && d_w_out) {
@@ -891,17 +909,12 @@ int apv_sweep_device(apv_handle* h, int n_mu, const double* mu, void* d_w_out, d
     rc = stage_sweep_multi(*h, n_mu, d_mu, (double*)d_w_out);
   }
   if (rc == OK && metrics_out) {
-    if (cudaMalloc((void**)&d_m, mc * sizeof(double)) != cudaSuccess) rc = fail(ECUDA, "cudaMalloc failed");
-    if (rc == OK) {
-      cudaMemsetAsync(d_m, 0, mc * sizeof(double), h->st);
-      rc = stage_sweep_metrics(*h, n_mu, d_mu, d_m);
-    }
-    if (rc == OK && cudaMemcpyAsync(metrics_out, d_m, mc * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess)
+    cudaMemsetAsync(h->sw_m, 0, mc * sizeof(double), h->st);
+    rc = stage_sweep_metrics(*h, n_mu, d_mu, h->sw_m);
+    if (rc == OK && cudaMemcpyAsync(metrics_out, h->sw_m, mc * sizeof(double), cudaMemcpyDeviceToHost, h->st) != cudaSuccess)
       rc = fail(ECUDA, "metrics copy failed");
   }
-  cudaStreamSynchronize(h->st);
-  cudaFree(d_mu);
-  if (d_m) cudaFree(d_m);
+  if (cudaStreamSynchronize(h->st) != cudaSuccess && rc == OK) rc = fail(ECUDA, "sweep failed: %s", cudaGetErrorString(cudaGetLastError()));
   return rc;
 }
 

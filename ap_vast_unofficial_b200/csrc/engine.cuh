@@ -39,6 +39,8 @@ struct JdiagWs {
   double* iv = nullptr;     // [nz][6][n][Vp] inverse-iteration work (interleaved over vectors)
   double* Zt = nullptr;     // [nz][V][n] eigenvectors of T -> of C -> joint eigenvectors U (row v)
   int* info = nullptr;      // [nz][4]: [0] first non-positive pivot (1-based, 0 = ok) [1] eig flags
+  double* dcw = nullptr;    // divide-and-conquer scratch (dc.cu; allocated on first use)
+  size_t dcw_count = 0;
   double* q1agg = nullptr;  // aggregated block reflectors + scratch of the GEMM back-transformation (allocated on first use)
   size_t q1agg_count = 0;
   double* ts2 = nullptr;    // two-stage tridiagonalisation scratch (band.cu): V panel, Y slices, X, S partials, T, band, flags
@@ -65,7 +67,10 @@ int twostage_nsplit_max();
 int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches);
 int twostage_apply_q1(JdiagWs& ws, cudaStream_t st, int* launches);   // then by the stage-1 block reflectors -> Zt
-int twostage_apply_q1_gemm(JdiagWs& ws, cudaStream_t st, int* launches);   // many vectors: DMMA GEMMs, in place in iv slot 4
+int twostage_apply_q1_gemm(JdiagWs& ws, cudaStream_t st, int* launches);
+// dc.cu: all n eigenpairs of the tridiagonal matrix (dd, ee) by divide and conquer -> lam (descending), iv slot 4
+bool dc_supported(int n);
+int dc_run(JdiagWs& ws, cudaStream_t st, int* launches);   // many vectors: DMMA GEMMs, in place in iv slot 4
 // regv != nullptr: per-zone diagonal loading read from device memory instead of `reg`.
 int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const dark[2], int ld_in, double reg,
               cudaStream_t st, int* launches, const double* regv = nullptr);
@@ -138,6 +143,9 @@ struct Handle {
   double* d_out_t = nullptr; // [2][H]
   double* h_pin = nullptr;   // pinned host staging
   size_t h_pin_count = 0;
+  double* sw_mu = nullptr;   // persistent scratch of the mu sweep (cudaMalloc / cudaFree per call cost up to 0.4 s)
+  double* sw_m = nullptr;
+  size_t sw_mu_cap = 0, sw_m_cap = 0;
   double* home_W = nullptr;  // the buffers W / d_out / d_out_t point at outside a multi-block call
   double* home_out = nullptr;
   double* home_out_t = nullptr;

@@ -1165,7 +1165,7 @@ int jdiag_alloc(JdiagWs& ws, int n, int V, int nz, int eig_mode) {
 
 void jdiag_free(JdiagWs& ws) {
   void* ps[] = {ws.Lm, ws.Cm, ws.Tm, ws.VH, ws.Dinv, ws.Z1, ws.Z2, ws.tau, ws.dd, ws.ee, ws.colbuf,
-                ws.ybuf, ws.wbuf, ws.tdws, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv, ws.q1agg};
+                ws.ybuf, ws.wbuf, ws.tdws, ws.Tf, ws.lam, ws.shift, ws.iv, ws.Zt, ws.info, ws.ts2, ws.SBinv, ws.q1agg, ws.dcw};
   for (void* p : ps)
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
@@ -1373,8 +1373,16 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   if (two_stage) APV_TRY(twostage_run(ws, st, &nl));
   else APV_TRY(tridiag_run(ws, st, &nl));
   APV_CUDA_TRY(cudaEventRecord(ws.ev[3], st));
-  // ---- top-V eigenpairs of T
+  // ---- eigenpairs of T
+  // many vectors (full-spectrum requests): one LANE per vector fills the chip; few vectors: one CTA per vector with the
+  // work arrays in shared memory (one CTA per SM, V / 148 waves of ~2.3 ms at n = 4096)
+  const bool many = (long long)V * nz >= 2048 && !getenv("APV_EIG_FEW");
+  // the whole spectrum of a two-stage problem: divide and conquer (dc.cu), its O(n^3) part on the tensor cores
+  const bool use_dc = many && two_stage && V == n && ws.Vp >= n && dc_supported(n) && !getenv("APV_EIG_NO_DC");
   double* tnorm = ws.shift + (size_t)nz * V;
+  if (use_dc) {
+    APV_TRY(dc_run(ws, st, &nl));
+  } else {
   if (V * nz <= 512) {
     APV_TRY(ensure_smem(eig_bisect_kernel<BIS_T>, (size_t)2 * n * sizeof(double)));
     eig_bisect_kernel<BIS_T><<<dim3(V, nz), BIS_T, (size_t)2 * n * sizeof(double), st>>>(ws.dd, ws.ee, ws.lam, tnorm, n, V);
@@ -1384,9 +1392,6 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   }
   eig_shift_kernel<<<nz, 32, 0, st>>>(ws.lam, ws.shift, V);
   const size_t ivsm = (size_t)6 * n * sizeof(double) + (size_t)round_up(n, 16);
-  // many vectors (full-spectrum requests): one LANE per vector fills the chip; few vectors: one CTA per vector with the
-  // work arrays in shared memory (one CTA per SM, V / 148 waves of ~2.3 ms at n = 4096)
-  const bool many = (long long)V * nz >= 2048 && !getenv("APV_EIG_FEW");
   if (ivsm <= 220 * 1024 && !many) {
     APV_TRY(ensure_smem(eig_invit_smem_kernel, ivsm));
     eig_invit_smem_kernel<<<dim3(V, nz), 128, ivsm, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
@@ -1394,6 +1399,7 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
     eig_invit_kernel<<<dim3(ws.Vp / 32, nz), 32, 0, st>>>(ws.dd, ws.ee, ws.shift, tnorm, ws.iv, ws.info, n, V, ws.Vp);
   }
   eig_cluster_mgs_kernel<<<nz, 256, 0, st>>>(ws.lam, tnorm, ws.iv, n, V, ws.Vp, 1e-6);
+  }
   APV_CUDA_TRY(cudaEventRecord(ws.ev[4], st));
   const bool gemm_bt = two_stage && many && n >= 512;
   if (gemm_bt) {

@@ -227,12 +227,18 @@ def test_multizone_per_zone_perceptual_weighting(Z):
     gpu.close()
 
 
-def test_full_spectrum_path_at_cfg2_size():
-    """V = n = 1024 on both zones: the many-vector route (lane-per-vector inverse iteration, aggregated block-reflector
-    GEMM back-transformation, GEMM back substitution; BASELINE cfg-4 semantics).  Checks: jdiag.m:33-35 identities,
+@pytest.mark.parametrize("solver", ["dc", "invit"])
+def test_full_spectrum_path_at_cfg2_size(solver, monkeypatch):
+    """V = n = 1024 on both zones: the many-vector route (divide and conquer on the tridiagonal matrix -- or, with
+    APV_EIG_NO_DC, multisection + lane-per-vector inverse iteration --, aggregated block-reflector GEMM
+    back-transformation, GEMM back substitution; BASELINE cfg-4 semantics).  Checks: jdiag.m:33-35 identities,
     the closed form w[V-1] = (R_B + mu (R_D + reg I))^-1 r_B (apVast.m:115-118), the one-launch mu sweep and its
     eigen-basis figures of merit against direct evaluation."""
     from ap_vast_unofficial_b200.workloads import make_workload
+    if solver == "invit":
+        monkeypatch.setenv("APV_EIG_NO_DC", "1")
+    else:
+        monkeypatch.delenv("APV_EIG_NO_DC", raising=False)
     wl = make_workload("cfg2", n_blocks=5)
     cfg = dict(wl["cfg"]); n = 1024
     cfg["number_of_eigenvectors"] = n
@@ -248,6 +254,9 @@ def test_full_spectrum_path_at_cfg2_size():
                                        (eng.R_B_to_B, eng.R_B_to_A, eng.U_B, eng.lambda_B, eng.r_B[:, 0], wB, 1)):
         assert np.all(np.diff(lam) <= 0)
         Bm = RD + 1e-7 * np.eye(n)
+        import scipy.linalg as sla
+        lref = sla.eigh(RB, Bm, eigvals_only=True)[::-1]
+        assert np.max(np.abs(lam - lref)) / lref[0] < 1e-11
         assert np.max(np.abs(U.T @ Bm @ U - np.eye(n))) < 1e-8
         assert np.max(np.abs(U.T @ RB @ U - np.diag(lam))) / lam[0] < 1e-8
         for k, mu in enumerate(mus):
