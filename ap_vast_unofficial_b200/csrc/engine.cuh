@@ -5,7 +5,7 @@
 
 namespace apv {
 
-constexpr int STATS_KC = 64;   // K chunk of the statistics SYRK; fixes the padding of the packed s' buffer
+constexpr int STATS_KC = 128;   // K chunk of the statistics SYRK; fixes the padding of the packed s' buffer
 
 // Derived sizes.  Symbols as in SURVEY.md: Nb block, H hop, K rir length, L srcs, M mics, J taps,
 // N statistics length, V ranks, n = L*J, P = N-J columns of the data matrix, F = Nb/2+1 bins.

@@ -20,8 +20,8 @@ namespace apv {
 namespace {
 
 constexpr int TM = 128;      // CTA tile (rows = cols)
-constexpr int KC = 64;       // K chunk per pipeline stage
-constexpr int FLUSH_CHUNKS = 4;   // DMMA accumulators are flushed into the shared-memory totals every 4 chunks (256 terms)
+constexpr int KC = STATS_KC; // K chunk per pipeline stage (128: half as many chunk boundaries -- mbarrier wait + CTA barrier -- as 64)
+constexpr int FLUSH_CHUNKS = 256 / KC;   // DMMA accumulators are flushed into the shared-memory totals every 256 terms
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier transaction counting: one elected thread stages the
 // 1-D segments of a pipeline stage; the copy engine fills shared memory while all warps issue DMMAs.
