@@ -1,7 +1,7 @@
 """NumPy prototype of the divide-and-conquer eigensolver for the symmetric tridiagonal matrix of the two-stage
 reduction (north_star (3); Cuppen's method with Gu-Eisenstat vector recomputation).  It has the SAME structure as
-csrc/dc.cu -- level-by-level merges, rank sort by counting, deflation scan, one secular root per thread by safeguarded
-Newton on the pole-free form, Loewner recomputation of z, dense merge matrix U~ and one GEMM per half -- so that every
+csrc/dc.cu -- level-by-level merges, rank sort by counting, deflation scan, one secular root per warp by the bracketed
+"middle way" iteration, Loewner recomputation of z, dense merge matrix U~ and one GEMM per half -- so that every
 kernel can be checked against its restatement here.
 
     python scripts/proto_dc.py            # self-test against scipy.linalg.eigh_tridiagonal
@@ -25,56 +25,58 @@ def split_diagonal(d, e, leaf=LEAF):
 
 def secular_root(dd, w, i, rho_total):
     """Root i of f(x) = 1 + sum_j w_j / (dd_j - x) in (dd_i, dd_{i+1}) (last: (dd_{m-1}, dd_{m-1} + rho_total]).
-    Returns (K, tau): x = dd_K + tau with tau accurate to a few ulps (so that dd_j - x = (dd_j - dd_K) - tau is accurate)."""
+    Returns (K, tau): x = dd_K + tau with tau accurate to a few ulps (so that dd_j - x = (dd_j - dd_K) - tau is accurate).
+    Bracketed "middle way" iteration (Li 1994 / LAPACK dlaed4): the poles left of the root (psi) and right of it (phi)
+    are each replaced by one pole at the interval end, matched in value and derivative; the two-pole equation is a
+    quadratic.  Same arithmetic as dc_secular_kernel."""
     m = dd.size
     last = i == m - 1
     if last:
-        K, Kp = i, -1
+        K = i
         lo, hi = 0.0, rho_total
     else:
         gap = dd[i + 1] - dd[i]
         mid = 0.5 * gap
         fm = 1.0 + np.sum(w / ((dd - dd[i]) - mid))
         if fm >= 0.0:
-            K, Kp = i, i + 1
+            K = i
             lo, hi = 0.0, mid
         else:
-            K, Kp = i + 1, i
+            K = i + 1
             lo, hi = -mid, 0.0
     delta = dd - dd[K]
-    mask = np.ones(m, bool)
-    mask[K] = False
-    if Kp >= 0:
-        mask[Kp] = False
-    dk, wk = delta[mask], w[mask]
-    wK = w[K]
-    dKp, wKp = (delta[Kp], w[Kp]) if Kp >= 0 else (0.0, 0.0)
-
-    def h(t):     # pole-free form of f and its derivative
-        q = dk - t
-        r = 1.0 + np.sum(wk / q)
-        rp = np.sum(wk / (q * q))
-        a = -t                       # delta_K - t = -t
-        if Kp >= 0:
-            b = dKp - t
-            return a * b * r + wK * b + wKp * a, -(a + b) * r + a * b * rp - wK - wKp
-        return a * r + wK, -r + a * rp
-
-    # f increases on the interval; h has the sign of f times (delta_K - t)(delta_K' - t), which is NEGATIVE inside
-    # an interior interval (one factor each sign) and negative*... : track the sign at the bracket ends instead
+    left = np.arange(m) <= i
     t = 0.5 * (lo + hi)
-    hlo_sign = None
     for it in range(200):
-        v, dv = h(t)
-        # sign of f at t:  interior interval: (dK - t)(dKp - t) < 0 always -> sign f = -sign h ; last: (dK - t) < 0 -> same
-        f_pos = v < 0.0
-        if v == 0.0:
+        q = 1.0 / (delta - t)
+        wq = w * q
+        psi, dpsi = np.sum(wq[left]), np.sum(wq[left] * q[left])
+        phi, dphi = np.sum(wq[~left]), np.sum(wq[~left] * q[~left])
+        f = 1.0 + psi + phi
+        if f == 0.0:
             break
-        if f_pos:
+        if f > 0.0:
             hi = t
         else:
             lo = t
-        tn = t - v / dv if dv != 0.0 else 0.5 * (lo + hi)
+        dl = delta[i] - t
+        qq, pp = dpsi * dl * dl, psi - dpsi * dl
+        if last:
+            c = 1.0 + pp
+            tn = delta[i] + qq / c if c != 0.0 else 0.5 * (lo + hi)
+        else:
+            dr = delta[i + 1] - t
+            ss, rr = dphi * dr * dr, phi - dphi * dr
+            c = 1.0 + pp + rr
+            qa, qb, qc = c, -(c * (dl + dr) + qq + ss), c * dl * dr + qq * dr + ss * dl
+            if qa == 0.0:
+                eta = -qc / qb if qb != 0.0 else 0.0
+            else:
+                sq = np.sqrt(max(qb * qb - 4.0 * qa * qc, 0.0))
+                e1 = (-qb + sq) / (2.0 * qa) if qb <= 0.0 else (-qb - sq) / (2.0 * qa)
+                e2 = qc / (qa * e1) if e1 != 0.0 else 0.0
+                eta = e1 if dl < e1 < dr else e2
+            tn = t + eta
         if not (lo < tn < hi):
             tn = 0.5 * (lo + hi)
         if tn == t or abs(tn - t) <= 2.0 * EPS * abs(tn):
