@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(double* __restrict__ sc
     // ~7 iterations on average instead of ~28 for Newton on the pole-free form (scripts/proto_dc.py).
     double t = 0.5 * (lo + hi);
     bool ok = false;
-    for (int it = 0; it < 200; ++it) {
+    for (int it = 0; it < 400; ++it) {
       double psi = 0.0, dpsi = 0.0, phi = 0.0, dphi = 0.0;
       for (int j = lane; j < m; j += 32) {
         const double qv = 1.0 / ((dd[j] - dK) - t);
@@ -335,7 +335,14 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(double* __restrict__ sc
         }
         tn = t + eta;
       }
-      if (!(lo < tn && tn < hi)) tn = 0.5 * (lo + hi);
+      if (!(lo < tn && tn < hi)) {
+        // bisection; geometric while the bracket still spans orders of magnitude (a root very close to its pole)
+        if (lo == 0.0) tn = hi * 0.015625;
+        else if (hi == 0.0) tn = lo * 0.015625;
+        else if (lo > 0.0 && hi > 4.0 * lo) tn = sqrt(lo * hi);
+        else if (hi < 0.0 && lo < 4.0 * hi) tn = -sqrt(lo * hi);
+        else tn = 0.5 * (lo + hi);
+      }
       if (tn == t || fabs(tn - t) <= 2.0 * DBL_EPSILON * fabs(tn)) { t = tn; ok = true; break; }
       t = tn;
       if (hi - lo <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi))) { ok = true; break; }

@@ -21,7 +21,8 @@ namespace {
 
 constexpr int TM = 128;      // CTA tile (rows = cols)
 constexpr int KC = STATS_KC; // K chunk per pipeline stage (128: half as many chunk boundaries -- mbarrier wait + CTA barrier -- as 64)
-constexpr int FLUSH_CHUNKS = 256 / KC;   // DMMA accumulators are flushed into the shared-memory totals every 256 terms
+constexpr int FLUSH_TERMS = 256;          // (512 was measured: S4 59.9 -> 59.4 ms, worst cfg-3 filter error 2.0e-9 -> 3.3e-9: not worth it)
+constexpr int FLUSH_CHUNKS = FLUSH_TERMS / KC;   // DMMA accumulators are flushed into the shared-memory totals every FLUSH_TERMS terms
 
 // TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier transaction counting: one elected thread stages the
 // 1-D segments of a pipeline stage; the copy engine fills shared memory while all warps issue DMMAs.

@@ -47,7 +47,7 @@ def secular_root(dd, w, i, rho_total):
     delta = dd - dd[K]
     left = np.arange(m) <= i
     t = 0.5 * (lo + hi)
-    for it in range(200):
+    for it in range(400):
         q = 1.0 / (delta - t)
         wq = w * q
         psi, dpsi = np.sum(wq[left]), np.sum(wq[left] * q[left])
@@ -78,7 +78,17 @@ def secular_root(dd, w, i, rho_total):
                 eta = e1 if dl < e1 < dr else e2
             tn = t + eta
         if not (lo < tn < hi):
-            tn = 0.5 * (lo + hi)
+            # bisection; geometric while the bracket still spans orders of magnitude (a root very close to its pole)
+            if lo == 0.0:
+                tn = hi * 0.015625
+            elif hi == 0.0:
+                tn = lo * 0.015625
+            elif lo > 0.0 and hi > 4.0 * lo:
+                tn = np.sqrt(lo * hi)
+            elif hi < 0.0 and lo < 4.0 * hi:
+                tn = -np.sqrt(lo * hi)
+            else:
+                tn = 0.5 * (lo + hi)
         if tn == t or abs(tn - t) <= 2.0 * EPS * abs(tn):
             t = tn
             break
