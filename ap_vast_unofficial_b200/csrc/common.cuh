@@ -1,6 +1,7 @@
 // Shared device/host helpers for the AP-VAST B200 engine (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -27,6 +28,13 @@ enum { OK = 0, EINVAL_ = 1, ENOTPD = 2, ECUDA = 3, ENOMEM_ = 4, ENOCONV = 5, ENC
   } while (0)
 
 extern thread_local char g_err[512];
+
+// NVTX range around the ENQUEUEING of a stage (header-only NVTX 3: a no-op unless a profiler is attached); the per-stage
+// device times come from CUDA events (apv_stage_times), the ranges label the launches in ncu / nsys timelines.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // cudaFuncSetAttribute belongs to the device context, not to the calling thread: bookkeeping per device ordinal.
 struct PerDevice {

@@ -135,13 +135,18 @@ namespace apv {
 // `skip_s1`: S1 was already run (split call).  `state_only`: warm-up of a block range, no statistics.
 int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1, bool state_only) {
   cudaEvent_t* ev = h.ev;
+  NvtxRange nv_front("apv front half: S1-S4");
   APV_CUDA_TRY(cudaEventRecord(ev[0], h.st));
-  if (!skip_s1) APV_TRY(stage_fir(h, d_inA, d_inB));
+  { NvtxRange nv("S1 rir_conv"); if (!skip_s1) APV_TRY(stage_fir(h, d_inA, d_inB)); }
   APV_CUDA_TRY(cudaEventRecord(ev[1], h.st));
-  if (!(skip_s1 && h.cfg.perceptual == 3)) APV_TRY(stage_targets(h, false));   // 3: S2 ran in apv_begin_block
-  APV_TRY(stage_weighted(h));
+  {
+    NvtxRange nv("S2+S3 wola_weight");
+    if (!(skip_s1 && h.cfg.perceptual == 3)) APV_TRY(stage_targets(h, false));   // 3: S2 ran in apv_begin_block
+    APV_TRY(stage_weighted(h));
+  }
   APV_CUDA_TRY(cudaEventRecord(ev[2], h.st));
   if (!state_only) {
+    NvtxRange nv("S4 stats_syrk");
     APV_TRY(stage_stats(h));
     if (h.cfg.loading_mode == 1) APV_TRY(stage_loading(h));
     else if (h.cfg.reg_relative && h.nz > 0) APV_TRY(stage_spectral_norms(h));
@@ -153,16 +158,17 @@ int run_front(Handle& h, const double* d_inA, const double* d_inB, bool skip_s1,
 // Back half: S5 (joint diagonalisation of the current slot), S6 (filter sum into h.W), S7 (rendering into h.d_out).
 int run_back(Handle& h, cudaEvent_t order) {
   cudaEvent_t* ev = h.ev;
+  NvtxRange nv_back("apv back half: S5-S7");
   APV_CUDA_TRY(cudaEventRecord(ev[7], h.st));
-  APV_TRY(run_jdiag(h));
+  { NvtxRange nv("S5 jdiag"); APV_TRY(run_jdiag(h)); }
   // with two back halves in flight the joint diagonalisations overlap, but S6 / S7 touch sequential state (the
   // published eigenpairs, the output overlap buffers G): they follow the previous block's
   if (order) APV_CUDA_TRY(cudaStreamWaitEvent(h.st, order, 0));
   APV_TRY(publish_eig(h));
   APV_CUDA_TRY(cudaEventRecord(ev[4], h.st));
-  APV_TRY(stage_sweep(h, h.cfg.mu, h.W));
+  { NvtxRange nv("S6 vast_sweep"); APV_TRY(stage_sweep(h, h.cfg.mu, h.W)); }
   APV_CUDA_TRY(cudaEventRecord(ev[5], h.st));
-  APV_TRY(stage_render(h));
+  { NvtxRange nv("S7 render_ola"); APV_TRY(stage_render(h)); }
   APV_CUDA_TRY(cudaEventRecord(ev[6], h.st));
   return OK;
 }
