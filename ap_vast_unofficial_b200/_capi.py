@@ -89,6 +89,7 @@ SIGNATURES = {
     "apv_bench_dmma_peak": (C.c_int, [C.c_int, _dp]),
     "apv_bench_dfma": (C.c_int, [C.c_int, _dp]),
     "apv_bench_gemm": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "apv_bench_gemm_shape": (C.c_int, [C.c_int] * 8 + [C.c_double, C.c_int, C.POINTER(C.c_float)]),
     "apv_last_error": (C.c_char_p, []),
     "apv_version": (C.c_char_p, []),
 }

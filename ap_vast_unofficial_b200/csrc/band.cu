@@ -495,6 +495,7 @@ struct SbChase {
   long long* dbg;      // APV_TS_DEBUG: clock64 totals of CTA 0 (compute step / barrier wait; loader store / wait / load)
 };
 #define CH_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (lane == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
+#define CH_FINE(k) do { if (fine) { const long long _t = clock64(); if (lane == 0) fine[k] += _t - tf; tf = _t; } } while (0)
 
 __device__ __forceinline__ int sweep_steps(int n, int s) { return (s <= n - 3) ? 1 + (n - s - 2) / NB2 : 0; }
 
@@ -531,7 +532,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   const int ngroups = (n - 2 + CGW - 1) / CGW;
   int* gprog = a.gprog + (size_t)z * ngroups;
   long long* dbgp = nullptr;
-  long long tk = clock64();
+  long long* fine = nullptr;              // phases inside a step: B warp of sweep 0 -> dbg[20..27], its D warp -> dbg[28..31]
+  long long tk = clock64(), tf = tk;
 
   // fetcher: rows [i0, i0 + 32) of the band -> window (zero rows beyond the matrix) once the previous group is past them
   auto load_chunk = [&](int g, int i0) {
@@ -580,6 +582,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   for (int g = cta; g < ngroups; g += G) {
     // debug clocks: the first group only (it never waits for a predecessor: the unthrottled pace of one time step)
     dbgp = (a.dbg && blockIdx.x == 0 && g == 0 && (wib == 0 || role >= 2)) ? a.dbg + 8 + (role >= 2 ? 4 * (role - 1) : 0) : nullptr;
+    fine = (a.dbg && blockIdx.x == 0 && g == 0 && wib < 2) ? a.dbg + (wib == 0 ? 20 : 28) : nullptr;
     tk = clock64();
     const int s0 = g * CGW;
     const int nst0 = sweep_steps(n, s0);
@@ -601,6 +604,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
         if (k >= 0 && k < nst) {
           const int q0 = s + 1 + k * NB2;       // rows of the step (k = 0: the first diagonal block)
           double* line = lines[wib];
+          if (fine) tf = clock64();
           if (role == 0) {
             double* myrow = win_row(win, q0 + lane);
             if (k == 0) {
@@ -614,6 +618,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
               double* pb = myrow + NB2 + lane;                        // B(lane, c) = pb[-c]
 #pragma unroll
               for (int c = 0; c < 32; ++c) B[c] = pb[-c];
+              CH_FINE(0);
               // B <- B H_prev
               bcast_store(line, v, lane);
               double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
@@ -629,11 +634,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
               const double y = tau * ((y0 + y1) + (y2 + y3));
               // the first column decides the new reflector: finish it first and hand it to the diagonal-block warp
               B[0] = fma(-y, line[0], B[0]);
+              CH_FINE(1);
               double vn, taun;
               warp_house(B[0], lane, vn, taun, beta);
+              CH_FINE(2);
               vline[wsw][lane] = vn;
               if (lane == 0) vline[wsw][32] = taun;
               pair_sync(1 + wsw);
+              CH_FINE(3);
 #pragma unroll
               for (int c = 2; c < 32; c += 2) {
                 const double2 vv = *reinterpret_cast<const double2*>(line + c);
@@ -643,11 +651,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
               B[1] = fma(-y, line[1], B[1]);
               v = vn; tau = taun;
               B[0] = (lane == 0) ? beta : 0.0;
+              CH_FINE(4);
               // B[:, 1:] <- H' B[:, 1:]
               double vals[32];
 #pragma unroll
               for (int c = 0; c < 32; ++c) vals[c] = v * B[c];
               const double u = tau * colsum32(vals, lane);       // lane c: tau v^T B[:, c]
+              CH_FINE(5);
               bcast_store(line, u, lane);
 #pragma unroll
               for (int c = 2; c < 32; c += 2) {
@@ -656,17 +666,23 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
                 B[c + 1] = fma(-v, uu.y, B[c + 1]);
               }
               B[1] = fma(-v, line[1], B[1]);
+              CH_FINE(6);
 #pragma unroll
               for (int c = 0; c < 32; ++c) pb[-c] = B[c];
+              CH_FINE(7);
             }
             if (q0 + lane < n) V2[(size_t)s * a.ldn + q0 + lane] = (lane == 0) ? tau : v;
           } else {
             // diagonal block: D <- H' D H'
             double D[32];
             win_load_diag(win, q0, lane, D);
+            CH_FINE(0);
             pair_sync(1 + wsw);
+            CH_FINE(1);
             two_sided32(D, vline[wsw][lane], vline[wsw][32], lane, line);
+            CH_FINE(2);
             win_store_diag(win, q0, lane, D);
+            CH_FINE(3);
           }
         }
         CH_TICK(0);
@@ -1214,6 +1230,8 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
             hc[0] * us, hc[1] * us, hc[2] * us, hc[3] * us, hc[4] * us, hc[5] * us, hc[6] * us);
     fprintf(stderr, "  chase us (first group): B-warp step %.0f | barrier %.0f ; storer: store+publish %.0f | barrier %.0f ; fetcher: wait %.0f | load %.0f | barrier %.0f\n",
             hc[8] * us, hc[11] * us, hc[12] * us, hc[15] * us, hc[17] * us, hc[18] * us, hc[19] * us);
+    fprintf(stderr, "  chase B warp us (first group): load B %.1f | y = B v %.1f | house %.1f | pair sync %.1f | B -= y v^T %.1f | column sums %.1f | B -= v u^T %.1f | store %.1f ; D warp: load %.1f | wait for the reflector %.1f | two-sided %.1f | store %.1f\n",
+            hc[20] * us, hc[21] * us, hc[22] * us, hc[23] * us, hc[24] * us, hc[25] * us, hc[26] * us, hc[27] * us, hc[28] * us, hc[29] * us, hc[30] * us, hc[31] * us);
   }
   return OK;
 }

@@ -482,7 +482,19 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->Sp, 4 * M * L * (size_t)D.Ns));
   TRYB(dalloc(&h->Wg, 2 * M * (size_t)D.F));
   TRYB(dalloc(&h->seed, 4 * L * L * (size_t)D.J));
-  if (cfg->stats_mode != 2) TRYB(dalloc(&h->Pbuf, 16 * n * (size_t)D.ldn));
+  if (cfg->stats_mode != 2) {
+    // microphones per SYRK launch: as many as 9 GB of partial matrices hold (16 at n = 4096, 4 at n = 8192); one launch
+    // over all the microphones has one partial last wave instead of four and no kernel boundary in between
+    const size_t per_mic = 4 * n * (size_t)D.ldn * sizeof(double);
+    const int gmax = std::min(16, (int)((M + 3) / 4 * 4));
+    int G = 4;
+    while (G + 4 <= gmax && (size_t)(G + 4) * per_mic <= (size_t)9200 * 1000 * 1000) G += 4;
+    if (const char* e = getenv("APV_SYRK_GROUP")) G = std::max(4, std::min(gmax, atoi(e) / 4 * 4));
+    h->syrk_group = G;
+    TRYB(dalloc(&h->Pbuf, (size_t)G * 4 * n * (size_t)D.ldn));
+    const size_t nt = (n + 127) / 128;
+    TRYB(dalloc(&h->syrk_cnt, 4 * (nt * (nt + 1) / 2)));
+  }
   TRYB(dalloc(&h->norms, 64));
   TRYB(dalloc(&h->pvec, 8 * n));
   TRYB(dalloc(&h->tframe, 2 * M * Nb));
@@ -577,7 +589,7 @@ void apv_destroy(apv_handle* h) {
   if (h->st_copy) cudaStreamSynchronize(h->st_copy);
   range_free(*h);
   void* ps[] = {h->rirT, h->rirTT, h->win, h->tw, h->G2, h->xin, h->Q, h->QT, h->O, h->OT, h->S, h->ST, h->Sp,
-                h->Wg, h->seed, h->Pbuf, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->regv,
+                h->Wg, h->seed, h->Pbuf, h->syrk_cnt, h->norms, h->pvec, h->tframe, h->tspec, h->G, h->Gt, h->regv,
                 h->lam, h->U, h->home_W, h->d_in, h->home_out, h->home_out_t, h->ring};
   for (void* p : ps)
     if (p) cudaFree(p);
@@ -1095,6 +1107,37 @@ int apv_bench_gemm(int n, int nrep, float* ms) {
   GemmArgs g{};
   g.A = dA; g.B = dB; g.C = dC; g.M = g.N = g.K = n; g.lda = g.ldb = g.ldc = n; g.alpha = 1.0; g.beta = 0.0; g.batch = 1;
   g.transB = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = gemm_f64(g, 0);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < nrep && rc == OK; ++i) rc = gemm_f64(g, 0);
+  cudaEventRecord(e1, 0);
+  if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(ECUDA, "gemm bench failed");
+  float t = 0.f;
+  cudaEventElapsedTime(&t, e0, e1);
+  *ms = t / nrep;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return rc;
+}
+
+int apv_bench_gemm_shape(int M, int N, int K, int batch, int transB, int tri, int mirror, int bn, double beta,
+                         int nrep, float* ms) {
+  if (M < 1 || N < 1 || K < 1 || batch < 1 || nrep < 1 || !ms) return fail(EINVAL_, "bad argument");
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  const size_t lda = (size_t)round_up(K, 2), ldb = transB ? lda : (size_t)round_up(N, 2), ldc = (size_t)round_up(N, 2);
+  const size_t ca = (size_t)M * lda, cb = transB ? (size_t)N * ldb : (size_t)K * ldb, cc = (size_t)M * ldc;
+  APV_CUDA_TRY(cudaMalloc((void**)&dA, batch * ca * sizeof(double)));
+  APV_CUDA_TRY(cudaMalloc((void**)&dB, batch * cb * sizeof(double)));
+  APV_CUDA_TRY(cudaMalloc((void**)&dC, batch * cc * sizeof(double)));
+  fill_kernel<<<256, 256>>>(dA, batch * ca, 1.0 / K);
+  fill_kernel<<<256, 256>>>(dB, batch * cb, 0.5);
+  fill_kernel<<<256, 256>>>(dC, batch * cc, 0.0);
+  GemmArgs g{};
+  g.A = dA; g.B = dB; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = (int)lda; g.ldb = (int)ldb; g.ldc = (int)ldc;
+  g.strideA = (long long)ca; g.strideB = (long long)cb; g.strideC = (long long)cc;
+  g.alpha = beta != 0.0 ? 1e-3 : 1.0; g.beta = beta; g.batch = batch; g.transB = transB; g.tri = tri; g.mirror = mirror; g.bn = bn;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   int rc = gemm_f64(g, 0);

@@ -108,7 +108,9 @@ struct Handle {
   double* seed = nullptr;    // [4][L][L][J]    first-row correlations (stats_mode 2)
   double* norms = nullptr;   // [4] spectral norms of the statistics (loading_mode 1) + power-iteration scratch
   double* pvec = nullptr;    // [2][4][n] power-iteration vectors
-  double* Pbuf = nullptr;    // [4 slices][4][n][ldn] per-microphone partial statistics (DMMA SYRK, tree-summed)
+  double* Pbuf = nullptr;    // [syrk_group slices][4][n][ldn] per-microphone partial statistics (DMMA SYRK, tree-summed)
+  int* syrk_cnt = nullptr;   // [4][lower tiles] arrival counters of the fused reduction (self-resetting)
+  int syrk_group = 4;        // microphones per SYRK launch (multiple of 4, at most 16; bounded by the size of Pbuf)
   double* Wg = nullptr;      // [2][M][F]
   double* tframe = nullptr;  // [2][M][Nb]
   double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)

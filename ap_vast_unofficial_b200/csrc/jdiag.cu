@@ -48,166 +48,189 @@ __global__ void prep_kernel(Ptr2 bright, Ptr2 dark, int ld_in, double* __restric
 // Cholesky of one diagonal block (<= NB x NB, NB = 64) and the inverse of its factor.  grid (nz), 128 threads.
 // The block is split 2 x 2 into 32 x 32 tiles; every tile operation is warp-synchronous with lane = row and the
 // row in registers, so the only CTA barriers are the eight phase boundaries (the first version eliminated column
-// by column with two CTA barriers per column: 94 us per block; this one 10 us):
+// by column with two CTA barriers per column: 94 us per block):
 //   L11 = chol(A11) | L21 = A21 L11^-T, X11 = L11^-1 | A22 -= L21 L21^T | L22 = chol(A22) |
 //   X22 = L22^-1, T = L21 X11 | X21 = -X22 T.
 // A non-positive (or NaN) pivot records its 1-based global index in info[z][0] (first one wins) and is replaced
 // by 1 so the launch sequence can finish; the host raises LinAlgError (numpy.linalg.cholesky, apvast.py:22-24).
 constexpr int CDP = NB + 1;      // shared-memory pitch
 
-// lane = row of a 32 x 32 symmetric tile held in a[] (entries c <= lane); on exit a[] holds the row of its Cholesky
-// factor.  col: 32 doubles of scratch; invd: reciprocals of the diagonal; returns the first bad pivot or -1.
-__device__ __forceinline__ int warp_chol32(double (&a)[32], int lane, double* col, double* invd) {
-  int bad = -1;
+// The kernel is launched 64 times per joint diagonalisation (n = 4096), each time on a cold instruction cache: a fully
+// unrolled version (13 000 SASS instructions, 200 KB) spent its 49 us streaming its own code at ~2 bytes per cycle
+// (in-kernel clocks: the phase times moved around with the data loads, their sum did not).  The eliminations are
+// therefore ROLLED loops over a rotating register window -- the current column is always a[0], the update of the
+// remaining columns and the shift are one FMA,  a[i] <- a[i+1] - m col[j+1+i]  -- and both halves of the 2 x 2
+// blocking run through the same code (loop over h): ~1000 instructions.
+
+// a[i] <- a[i+1] - m p[i]  for i < NI  (p: multipliers of the columns j+1 .. j+NI)
+template <int NI>
+__device__ __forceinline__ void rot_update(double (&a)[32], double m, const double* p) {
 #pragma unroll
+  for (int i = 0; i < NI; ++i) a[i] = fma(-m, p[i], a[i + 1]);
+}
+
+// lane = row of a 32 x 32 symmetric tile, a[i] = entry (lane, i) (entries i <= lane matter).  Writes the row of the
+// Cholesky factor to Srow[0 .. 32) (zeros above the diagonal) and the reciprocals of the diagonal to invd.
+// col: 64 doubles of scratch.  Returns the first bad pivot or -1.
+__device__ __forceinline__ int warp_chol32(double (&a)[32], int lane, double* col, double* invd, double* Srow) {
+  int bad = -1;
+  col[32 + lane] = 0.0;                     // multipliers of the columns beyond the tile
+#pragma unroll 1
   for (int j = 0; j < 32; ++j) {
-    double d = __shfl_sync(0xffffffffu, a[j], j);
+    double d = __shfl_sync(0xffffffffu, a[0], j);
     if (!(d > 0.0)) {                       // also catches NaN
       if (bad < 0) bad = j;
       d = 1.0;
     }
     const double inv = rsqrt(d);
-    const double l = (lane == j) ? d * inv : a[j] * inv;
-    a[j] = (lane >= j) ? l : 0.0;
-    __syncwarp();
-    col[lane] = a[j];
+    const double l = (lane == j) ? d * inv : a[0] * inv;
+    Srow[j] = (lane >= j) ? l : 0.0;
+    __syncwarp();                           // the previous column's multipliers have been read
+    col[lane] = l;
     if (lane == j) invd[j] = inv;
     __syncwarp();
-#pragma unroll
-    for (int c = j + 1; c < 32; ++c) a[c] = fma(-a[j], col[c], a[c]);   // (entries c > lane are never used)
+    // (rows lane < j are finished: what they compute from here on is never used)
+    if (j < 16) rot_update<31>(a, l, col + j + 1);
+    else rot_update<15>(a, l, col + j + 1);
+    a[31] = 0.0;
   }
   return bad;
 }
 
+// Forward substitution with a lower-triangular 32 x 32 tile Lt (pitch CDP, reciprocal diagonal invd), right-looking:
+//   x_j = a[0] invd[j];  a <- a[1:] - x_j Lt[j+1:, j].   x_j is written to out[j * ostride].
+// lane = row of A21 for L21 = A21 L11^-T (a = that row), lane = column of the inverse for X = Lt^-1 (a = e_lane).
+__device__ __forceinline__ void warp_trsolve32(double (&a)[32], const double* Lt, const double* invd, double* out,
+                                               int ostride) {
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const double x = a[0] * invd[j];
+    out[j * ostride] = x;
+    const double* lc = Lt + j;              // column j of the tile
+    // (rows beyond the tile are clamped to its last row: they only feed window entries that are never used)
+    if (j < 16) {
+#pragma unroll
+      for (int i = 0; i < 31; ++i) a[i] = fma(-x, lc[min(j + 1 + i, 31) * CDP], a[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 15; ++i) a[i] = fma(-x, lc[min(j + 1 + i, 31) * CDP], a[i + 1]);
+    }
+    a[31] = 0.0;
+  }
+}
+
+#ifdef APV_CD_DEBUG
+#define CD_INIT() long long cd_t[16]; int cd_n = 0; cd_t[cd_n++] = clock64()
+#define CD_TICK(i) cd_t[cd_n++] = clock64()
+#define CD_PRINT() do { if (threadIdx.x == 0 && blockIdx.x == 0 && k0 == 1024) { printf("chol_diag cycles:"); for (int q = 1; q < cd_n; ++q) printf(" %lld", cd_t[q] - cd_t[q - 1]); printf("\n"); } } while (0)
+#else
+#define CD_INIT()
+#define CD_TICK(i)
+#define CD_PRINT()
+#endif
 __global__ void __launch_bounds__(128) chol_diag_kernel(double* __restrict__ Lm, double* __restrict__ Dinv, int n,
                                                         int ldn, int k0, int nbk, int nblk, int* __restrict__ info) {
   extern __shared__ double cd_sm[];
+  CD_INIT();
   double (*S)[CDP] = reinterpret_cast<double (*)[CDP]>(cd_sm);               // A -> L (lower)
   double (*X)[CDP] = reinterpret_cast<double (*)[CDP]>(cd_sm + NB * CDP);    // L^-1 (lower)
   __shared__ double Tm_[32][33];         // L21 X11
   __shared__ double invd[NB];
-  __shared__ double cols[2][32];
+  __shared__ double cols[64];
   const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* A = Lm + (size_t)z * n * ldn + (size_t)k0 * ldn + k0;
-  for (int i = tid; i < NB * NB; i += 128) {
-    const int r = i / NB, c = i % NB;
-    S[r][c] = (c <= r) ? ((r < nbk && c < nbk) ? A[(size_t)r * ldn + c] : (r == c ? 1.0 : 0.0)) : 0.0;
-    X[r][c] = 0.0;
-  }
-  __syncthreads();
-  double a[32];
-  // ---- L11
-  if (warp == 0) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
-    const int bad = warp_chol32(a, lane, cols[0], invd);
-    if (bad >= 0 && bad < nbk && lane == 0 && info[z * 4] == 0) info[z * 4] = k0 + bad + 1;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) S[lane][c] = (c <= lane) ? a[c] : 0.0;
-  }
-  __syncthreads();
-  // ---- L21 = A21 L11^-T (warp 1, lane = row of A21);  X11 = L11^-1 (warp 2, lane = column of X11)
-  if (warp == 1) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][c];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      double t = a[j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) t = fma(-a[k], S[j][k], t);
-      a[j] = t * invd[j];
-    }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) S[32 + lane][c] = a[c];
-  } else if (warp == 2) {
-    // column `lane` of X11: x_r = (delta_{r,lane} - sum_{k<r} L[r][k] x_k) / L[r][r], zero above the diagonal
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      double t = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < r; ++k) t = fma(-S[r][k], a[k], t);
-      a[r] = (r >= lane) ? t * invd[r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < 32; ++r) X[r][lane] = a[r];
-  }
-  __syncthreads();
-  // ---- A22 -= L21 L21^T: lane = row, every warp eight columns
   {
-    double l[32];
+    // all 32 loads of a thread in flight together (one after the other they cost one L2 round trip each)
+    double v[NB * NB / 128];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
+    for (int u = 0; u < NB * NB / 128; ++u) {
+      const int i = tid + 128 * u, r = i / NB, c = i % NB;
+      v[u] = (c <= r) ? ((r < nbk && c < nbk) ? A[(size_t)r * ldn + c] : (r == c ? 1.0 : 0.0)) : 0.0;
+    }
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      const int c = warp * 8 + cc;
-      double t0 = 0.0, t1 = 0.0;
+    for (int u = 0; u < NB * NB / 128; ++u) {
+      const int i = tid + 128 * u, r = i / NB, c = i % NB;
+      S[r][c] = v[u];
+      X[r][c] = 0.0;
+    }
+  }
+  __syncthreads();
+  CD_TICK(0);
+  double a[32];
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int o = 32 * h;
+    if (warp == 0) {
+      // ---- L_hh = chol(A_hh)  (h = 1: A22 has taken its update)
 #pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        t0 = fma(l[k], S[32 + c][k], t0);
-        t1 = fma(l[k + 1], S[32 + c][k + 1], t1);
+      for (int c = 0; c < 32; ++c) a[c] = S[o + lane][o + c];
+      const int bad = warp_chol32(a, lane, cols, invd + o, &S[o + lane][o]);
+      if (bad >= 0 && o + bad < nbk && lane == 0 && info[z * 4] == 0) info[z * 4] = k0 + o + bad + 1;
+    } else if (h == 1 && (warp == 1 || warp == 3)) {
+      // ---- T = L21 X11 beside the factorisation of A22: lane = row, 16 columns per warp
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a[k] = S[32 + lane][k];
+      const int c0 = (warp == 1) ? 0 : 16;
+#pragma unroll 1
+      for (int cc = 0; cc < 16; ++cc) {
+        const int c = c0 + cc;
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          t0 = fma(a[k], X[k][c], t0);
+          t1 = fma(a[k + 1], X[k + 1][c], t1);
+        }
+        Tm_[lane][c] = t0 + t1;
       }
-      if (c <= lane) S[32 + lane][32 + c] -= t0 + t1;
     }
-  }
-  __syncthreads();
-  // ---- L22
-  if (warp == 0) {
+    __syncthreads();
+    CD_TICK(1);
+    if (warp == 2 || (warp == 1 && h == 0)) {
+      // ---- warp 2: X_hh = L_hh^-1 (lane = column);  warp 1 (h = 0): L21 = A21 L11^-T (lane = row of A21)
+      const bool inverse = warp == 2;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
-    const int bad = warp_chol32(a, lane, cols[0], invd + 32);
-    if (bad >= 0 && 32 + bad < nbk && lane == 0 && info[z * 4] == 0) info[z * 4] = k0 + 32 + bad + 1;
+      for (int c = 0; c < 32; ++c) a[c] = inverse ? (c == lane ? 1.0 : 0.0) : S[32 + lane][c];
+      warp_trsolve32(a, &S[o][o], invd + o, inverse ? &X[o][o + lane] : &S[32 + lane][0], inverse ? CDP : 1);
+    }
+    __syncthreads();
+    CD_TICK(2);
+    if (h == 0) {
+      // ---- A22 -= L21 L21^T: lane = row, every warp eight columns
 #pragma unroll
-    for (int c = 0; c < 32; ++c) S[32 + lane][32 + c] = (c <= lane) ? a[c] : 0.0;
-  } else if (warp == 1 || warp == 3) {
-    // T = L21 X11, lane = row, 16 columns per warp:  T[r][c] = sum_{k >= c} L21[r][k] X11[k][c]
-    double l[32];
+      for (int k = 0; k < 32; ++k) a[k] = S[32 + lane][k];
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        const int c = warp * 8 + cc;
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
-    const int c0 = (warp == 1) ? 0 : 16;
-#pragma unroll
-    for (int cc = 0; cc < 16; ++cc) {
-      const int c = c0 + cc;
-      double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        t0 = fma(l[k], X[k][c], t0);
-        t1 = fma(l[k + 1], X[k + 1][c], t1);
+        for (int k = 0; k < 32; k += 2) {
+          t0 = fma(a[k], S[32 + c][k], t0);
+          t1 = fma(a[k + 1], S[32 + c][k + 1], t1);
+        }
+        if (c <= lane) S[32 + lane][32 + c] -= t0 + t1;
       }
-      Tm_[lane][c] = t0 + t1;
+      __syncthreads();
+      CD_TICK(3);
     }
   }
-  __syncthreads();
-  // ---- X22 = L22^-1 (warp 2)
-  if (warp == 2) {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      double t = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < r; ++k) t = fma(-S[32 + r][32 + k], a[k], t);
-      a[r] = (r >= lane) ? t * invd[32 + r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < 32; ++r) X[32 + r][32 + lane] = a[r];
-  }
-  __syncthreads();
   // ---- X21 = -X22 T: lane = row, eight columns per warp
   {
-    double xr[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) xr[k] = X[32 + lane][32 + k];
-#pragma unroll
+    for (int k = 0; k < 32; ++k) a[k] = X[32 + lane][32 + k];
+#pragma unroll 1
     for (int cc = 0; cc < 8; ++cc) {
       const int c = warp * 8 + cc;
       double t0 = 0.0, t1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 32; k += 2) {
-        t0 = fma(xr[k], Tm_[k][c], t0);
-        t1 = fma(xr[k + 1], Tm_[k + 1][c], t1);
+        t0 = fma(a[k], Tm_[k][c], t0);
+        t1 = fma(a[k + 1], Tm_[k + 1][c], t1);
       }
       X[32 + lane][c] = -(t0 + t1);
     }
   }
   __syncthreads();
+  CD_TICK(4);
   double* Di = Dinv + ((size_t)z * nblk + k0 / NB) * NB * NB;
   for (int i = tid; i < NB * NB; i += 128) {
     const int r = i / NB, c = i % NB;
@@ -215,6 +238,8 @@ __global__ void __launch_bounds__(128) chol_diag_kernel(double* __restrict__ Lm,
     if (r < nbk && c < nbk) A[(size_t)r * ldn + c] = (c <= r) ? S[r][c] : 0.0;
     Di[i] = in ? X[r][c] : 0.0;
   }
+  CD_TICK(5);
+  CD_PRINT();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1261,11 +1286,25 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
   const int nblk = ceil_div(n, NB);
   const size_t chol_smem = (size_t)2 * NB * CDP * sizeof(double);
   APV_TRY(ensure_smem(chol_diag_kernel, chol_smem));
+  // APV_CHOL_DEBUG=1: synchronous per-kernel-class times of the factorisation (diagonal blocks | panels | updates inside
+  // a super-block | trailing updates), printed to stderr
+  const bool cdbg = getenv("APV_CHOL_DEBUG") != nullptr;
+  cudaEvent_t ce0 = nullptr, ce1 = nullptr;
+  double cacc[4] = {0, 0, 0, 0};
+  if (cdbg) { cudaEventCreate(&ce0); cudaEventCreate(&ce1); }
+  auto cbegin = [&]() { if (cdbg) cudaEventRecord(ce0, st); };
+  auto cend = [&](int k) {
+    if (!cdbg) return;
+    cudaEventRecord(ce1, st); cudaEventSynchronize(ce1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, ce0, ce1); cacc[k] += ms;
+  };
   for (int s0 = 0; s0 < n; s0 += SB) {
     const int s1 = std::min(n, s0 + SB);
     for (int k0 = s0; k0 < s1; k0 += NB) {
       const int nbk = std::min(NB, n - k0);
+      cbegin();
       chol_diag_kernel<<<nz, 128, chol_smem, st>>>(ws.Lm, ws.Dinv, n, ldn, k0, nbk, nblk, ws.info);
+      cend(0);
       ++nl;
       const int below = n - k0 - nbk;
       if (below > 0) {
@@ -1275,7 +1314,9 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
         p.B = ws.Dinv + (size_t)(k0 / NB) * NB * NB; p.ldb = NB; p.strideB = (long long)nblk * NB * NB;
         p.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0; p.ldc = ldn; p.strideC = mstride;
         p.M = below; p.N = nbk; p.K = nbk; p.transB = 1; p.alpha = 1.0; p.beta = 0.0;
+        cbegin();
         APV_TRY(gemm_f64(p, st));
+        cend(1);
         ++nl;
         const int cols = s1 - k0 - nbk;      // remaining columns of the super-block
         if (cols > 0) {
@@ -1285,7 +1326,9 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
           u.B = p.C; u.ldb = ldn; u.strideB = mstride;
           u.C = ws.Lm + (size_t)(k0 + nbk) * ldn + k0 + nbk; u.ldc = ldn; u.strideC = mstride;
           u.M = below; u.N = cols; u.K = nbk; u.transB = 1; u.alpha = -1.0; u.beta = 1.0;
+          cbegin();
           APV_TRY(gemm_f64(u, st));
+          cend(2);
           ++nl;
         }
       }
@@ -1297,9 +1340,16 @@ int jdiag_run(JdiagWs& ws, const double* const bright[2], const double* const da
       u.B = u.A; u.ldb = ldn; u.strideB = mstride;
       u.C = ws.Lm + (size_t)s1 * ldn + s1; u.ldc = ldn; u.strideC = mstride;
       u.M = n - s1; u.N = n - s1; u.K = s1 - s0; u.transB = 1; u.tri = 1; u.alpha = -1.0; u.beta = 1.0;
+      cbegin();
       APV_TRY(gemm_f64(u, st));
+      cend(3);
       ++nl;
     }
+  }
+  if (cdbg) {
+    fprintf(stderr, "cholesky ms: diagonal blocks %.2f | panels %.2f | super-block updates %.2f | trailing updates %.2f\n",
+            cacc[0], cacc[1], cacc[2], cacc[3]);
+    cudaEventDestroy(ce0); cudaEventDestroy(ce1);
   }
 
   APV_CUDA_TRY(cudaEventRecord(ws.ev[1], st));

@@ -20,6 +20,7 @@ namespace apv {
 namespace {
 
 constexpr int TM = 128;      // CTA tile (rows = cols)
+constexpr int SYRK_MAX_GROUP = 16;   // microphones per SYRK launch (their partial tiles are summed by the last CTA of a tile)
 constexpr int KC = STATS_KC; // K chunk per pipeline stage (128: half as many chunk boundaries -- mbarrier wait + CTA barrier -- as 64)
 constexpr int FLUSH_TERMS = 256;          // (512 was measured: S4 59.9 -> 59.4 ms, worst cfg-3 filter error 2.0e-9 -> 3.3e-9: not worth it)
 constexpr int FLUSH_CHUNKS = FLUSH_TERMS / KC;   // DMMA accumulators are flushed into the shared-memory totals every FLUSH_TERMS terms
@@ -75,7 +76,8 @@ __global__ void pack_stats_kernel(const double* __restrict__ S, double* __restri
 // plus one zero segment used by out-of-range rows.
 __global__ void __launch_bounds__(256, 1)
 syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, Dims D, int ntile, int SEG, int maxl,
-                     unsigned path_mask, int m_first, int m_count, int comp) {
+                     unsigned path_mask, int m_first, int m_count, int comp, double* __restrict__ R,
+                     int* __restrict__ tile_cnt, int MA, int first) {
   // blockIdx.z = microphone slice: the K dimension (microphones x P) is split per microphone and the per-microphone
   // partial matrices are added up by a tree (syrk_reduce_kernel) -- a fixed-order accumulation over all M P terms
   // would leave R with ~1e-14 relative rounding error, which the ill-conditioned pencil amplifies beyond the
@@ -87,6 +89,9 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
   if (!((path_mask >> path) & 1u)) return;
   const int mslice = blockIdx.z;
   if (mslice >= m_count) return;
+  // paths into zone A (0: A->A, 2: B->A) stop at the last real microphone of zone A (MA)
+  const bool zoneA = (path & 1) == 0;
+  if (zoneA && m_first + mslice >= MA) return;
   // decode linear lower-triangle tile index -> (bi, bj), bi >= bj
   int t = blockIdx.x, bi = 0;
   while (t >= bi + 1) { t -= bi + 1; ++bi; }
@@ -239,32 +244,76 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
       }
     }
   }
-}
 
-// R (+)= tree sum of the per-microphone partial matrices of one group; the last group also mirrors the lower
-// triangle so that R is stored as a full symmetric matrix.  grid (lower tiles, 4 paths), 256 threads.
-__global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* __restrict__ Pbuf, double* __restrict__ R, Dims D,
-                                                          unsigned path_mask, int m_count, int first, int last) {
-  const int path = blockIdx.y;
-  if (!((path_mask >> path) & 1u)) return;
-  int t = blockIdx.x, bi = 0;
-  while (t >= bi + 1) { t -= bi + 1; ++bi; }
-  const int bj = t;
-  const int n = D.n, ldn = D.ldn;
-  const size_t ps = (size_t)4 * n * ldn;                        // slice stride
-  const double* P0 = Pbuf + (size_t)path * n * ldn;
-  double* Rp = R + (size_t)path * n * ldn;
-  for (int e = threadIdx.x; e < TM * TM; e += 256) {
-    const int r = bi * TM + e / TM, c = bj * TM + (e % TM);
-    if (r >= n || c >= n || c > r) continue;
-    const size_t o = (size_t)r * ldn + c;
-    double v[4];
+  // ---- fused reduction: the LAST microphone slice of this launch to finish the tile adds the partial tiles up
+  // (threadfence + counter; the order of the sum is fixed by the code below, not by the order of arrival, so R is
+  // bit-reproducible): groups of four microphones as trees (v0 + v1) + (v2 + v3), the groups one after the other,
+  // on top of what earlier launches left in R.  The launch that holds the last microphone of the path also mirrors
+  // the lower triangle.  (Round 2 used a separate syrk_reduce_kernel per group of four microphones: 4 launches that
+  // re-read R and left the tensor pipe idle for 1.3 ms per block, plus the tail of a SYRK launch in front of each.)
+  __shared__ int s_last;
+  const int contributors = zoneA ? min(m_count, MA - m_first) : m_count;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(&tile_cnt[path * ntile + blockIdx.x], 1);
+    s_last = (old == contributors - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) tile_cnt[path * ntile + blockIdx.x] = 0;            // ready for the next launch
+  const bool mirror = zoneA ? (m_first + m_count >= MA) : (m_first + m_count >= D.M);
+  const size_t ps = (size_t)4 * n * D.ldn;                          // slice stride
+  const double* P0 = Pbuf + (size_t)path * n * D.ldn;
+  double* Rp = R + (size_t)path * n * D.ldn;
+  // thread -> two consecutive columns of one row; 64 column pairs x 4 rows, two rows per thread and pass; all the
+  // partial tiles of a pass are in flight together (the accumulators are dead: there is room for 2 x 16 pairs)
+  const int cp2 = (tid & 63) * 2, rr = tid >> 6;
+  for (int rb = 0; rb < TM; rb += 8) {
+    double2 v[2][SYRK_MAX_GROUP];
+    double2 sum[2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = q < m_count ? P0[q * ps + o] : 0.0;
-    double s = (v[0] + v[1]) + (v[2] + v[3]);
-    if (!first) s += Rp[o];
-    Rp[o] = s;
-    if (last && c != r) Rp[(size_t)c * ldn + r] = s;
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + rb + rr + 4 * u, c = c0 + cp2;
+      const bool ok = r < n && c <= r;        // (c is even and ldn is even: the pair stays inside the row)
+      const double* src = P0 + (size_t)r * D.ldn + c;
+#pragma unroll
+      for (int q = 0; q < SYRK_MAX_GROUP; ++q)
+        v[u][q] = (ok && q < contributors) ? __ldcg(reinterpret_cast<const double2*>(src + (size_t)q * ps))
+                                           : make_double2(0.0, 0.0);
+      sum[u] = (ok && !first) ? *reinterpret_cast<const double2*>(Rp + (size_t)r * D.ldn + c) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int g = 0; g < SYRK_MAX_GROUP / 4; ++g) {
+        if (4 * g >= contributors) break;
+        const double gx = (v[u][4 * g].x + v[u][4 * g + 1].x) + (v[u][4 * g + 2].x + v[u][4 * g + 3].x);
+        const double gy = (v[u][4 * g].y + v[u][4 * g + 1].y) + (v[u][4 * g + 2].y + v[u][4 * g + 3].y);
+        if (g == 0 && first) {
+          sum[u] = make_double2(gx, gy);
+        } else {
+          sum[u].x = gx + sum[u].x;
+          sum[u].y = gy + sum[u].y;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = r0 + rb + rr + 4 * u, c = c0 + cp2;
+      if (r >= n || c > r) continue;
+      // the partial tiles hold the lower triangle only: the second element of a pair on the diagonal is not part of it
+      if (c + 1 <= r) {
+        *reinterpret_cast<double2*>(Rp + (size_t)r * D.ldn + c) = sum[u];
+        if (mirror) {
+          Rp[(size_t)c * D.ldn + r] = sum[u].x;
+          Rp[(size_t)(c + 1) * D.ldn + r] = sum[u].y;
+        }
+      } else {
+        Rp[(size_t)r * D.ldn + c] = sum[u].x;
+      }
+    }
   }
 }
 
@@ -555,20 +604,14 @@ int stage_stats(Handle& h) {
   // paths into zone A (0: A->A, 2: B->A) stop at the last real microphone of zone A (silent padding microphones of
   // the multi-zone composition contribute nothing); groups of four microphones
   const int MA = (h.cfg.active_mics_A > 0 && h.cfg.active_mics_A < D.M) ? round_up(h.cfg.active_mics_A, 4) : D.M;
-  for (int m0 = 0; m0 < D.M; m0 += 4) {
-    const int mc = std::min(4, D.M - m0);
+  const int G = h.syrk_group;
+  for (int m0 = 0; m0 < D.M; m0 += G) {
+    const int mc = std::min(G, D.M - m0);
     const unsigned mA = m0 < MA ? (pmask & 0x5u) : 0u, mB = pmask & 0xAu;
     if ((mA | mB) == 0u) continue;
-    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc, comp);
-    const bool lastA = m0 + 4 >= MA, lastB = m0 + 4 >= D.M;
-    if (mA && mB && lastA != lastB) {
-      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mA, mc, m0 == 0, lastA);
-      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mB, mc, m0 == 0, lastB);
-      ++nl;
-    } else {
-      syrk_reduce_kernel<<<dim3(ntile, 4), 256, 0, h.st>>>(h.Pbuf, h.R, D, mA | mB, mc, m0 == 0, mA ? lastA : lastB);
-    }
-    nl += 2;
+    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc, comp,
+                                                                h.R, h.syrk_cnt, MA, m0 == 0);
+    ++nl;
   }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));
   rvec_kernel<<<dim3(ceil_div(D.n, 8), 2), 256, 0, h.st>>>(h.Sp, h.ST, h.rvec, D, zmask);

@@ -254,6 +254,11 @@ int apv_bench_dmma_peak(int iters, double* tflops);
 int apv_bench_dfma(int iters, double* out3);
 /* Times nrep launches of the internal GEMM (M=N=K=n) on device data; returns ms per launch. */
 int apv_bench_gemm(int n, int nrep, float* ms);
+/* One shape of the same building block: C (M x N) = alpha A B(^T) + beta C with K columns, `batch` independent
+ * problems, optionally only the lower tiles (tri) stored to both triangles (mirror); bn = forced tile width (0 = auto).
+ * Shapes of the joint diagonalisation: rank-64 band updates, rank-256 trailing updates, skinny products. */
+int apv_bench_gemm_shape(int M, int N, int K, int batch, int transB, int tri, int mirror, int bn, double beta,
+                         int nrep, float* ms);
 
 const char* apv_last_error(void);
 const char* apv_version(void);
