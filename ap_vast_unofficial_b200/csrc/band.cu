@@ -1200,7 +1200,8 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       // groups in flight: a group lasts n / NB2 + 2 CGW time steps and the next one starts 2 CGW + 1 steps later
       const int ngroups = ceil_div(n - 2, CGW);
       const int want = ceil_div(n / NB2 + 2 * CGW, 2 * CGW + 1) + 4;
-      const int G = std::max(1, std::min(std::min(sms / nz, want), ngroups));
+      int G = std::max(1, std::min(std::min(sms / nz, want), ngroups));
+      if (const char* e = getenv("APV_CHASE_G")) G = std::max(1, std::min(std::min(sms / nz, atoi(e)), ngroups));   // (experiment)
       const size_t smem = (size_t)CG_NSLOT * CG_PITCH * sizeof(double);
       static PerDevice pd_configured; size_t& configured = pd_configured.cur();
       if (!configured) {

@@ -483,17 +483,14 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   TRYB(dalloc(&h->Wg, 2 * M * (size_t)D.F));
   TRYB(dalloc(&h->seed, 4 * L * L * (size_t)D.J));
   if (cfg->stats_mode != 2) {
-    // microphones per SYRK launch: as many as 9 GB of partial matrices hold (16 at n = 4096, 4 at n = 8192); one launch
-    // over all the microphones has one partial last wave instead of four and no kernel boundary in between
-    const size_t per_mic = 4 * n * (size_t)D.ldn * sizeof(double);
-    const int gmax = std::min(16, (int)((M + 3) / 4 * 4));
-    int G = 4;
-    while (G + 4 <= gmax && (size_t)(G + 4) * per_mic <= (size_t)9200 * 1000 * 1000) G += 4;
-    if (const char* e = getenv("APV_SYRK_GROUP")) G = std::max(4, std::min(gmax, atoi(e) / 4 * 4));
+    // microphones per SYRK launch (their partial tiles of one (tile, path) share a ring slot) and ring length
+    int G = std::min(16, (int)M);
+    if (const char* e = getenv("APV_SYRK_GROUP")) G = std::max(1, std::min(16, atoi(e)));
     h->syrk_group = G;
-    TRYB(dalloc(&h->Pbuf, (size_t)G * 4 * n * (size_t)D.ldn));
+    if (const char* e = getenv("APV_SYRK_SLOTS")) h->syrk_slots = std::max(2, atoi(e));
+    TRYB(dalloc(&h->Pbuf, (size_t)h->syrk_slots * 16 * 128 * 128));
     const size_t nt = (n + 127) / 128;
-    TRYB(dalloc(&h->syrk_cnt, 4 * (nt * (nt + 1) / 2)));
+    TRYB(dalloc(&h->syrk_cnt, 4 * (nt * (nt + 1) / 2) + (size_t)h->syrk_slots));
   }
   TRYB(dalloc(&h->norms, 64));
   TRYB(dalloc(&h->pvec, 8 * n));

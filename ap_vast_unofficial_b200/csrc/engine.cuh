@@ -108,9 +108,10 @@ struct Handle {
   double* seed = nullptr;    // [4][L][L][J]    first-row correlations (stats_mode 2)
   double* norms = nullptr;   // [4] spectral norms of the statistics (loading_mode 1) + power-iteration scratch
   double* pvec = nullptr;    // [2][4][n] power-iteration vectors
-  double* Pbuf = nullptr;    // [syrk_group slices][4][n][ldn] per-microphone partial statistics (DMMA SYRK, tree-summed)
-  int* syrk_cnt = nullptr;   // [4][lower tiles] arrival counters of the fused reduction (self-resetting)
-  int syrk_group = 4;        // microphones per SYRK launch (multiple of 4, at most 16; bounded by the size of Pbuf)
+  double* Pbuf = nullptr;    // [syrk_slots][16 slices][128][128] ring of per-microphone partial tiles (DMMA SYRK, tree-summed)
+  int* syrk_cnt = nullptr;   // [4][lower tiles] arrival counters of the fused reduction (self-resetting) + [syrk_slots] ring state
+  int syrk_group = 16;       // microphones per SYRK launch (at most 16)
+  int syrk_slots = 16;       // ring slots (16 x 2 MB: stays in L2; 12 and 24 measure the same, 48 is 1.7 ms slower)
   double* Wg = nullptr;      // [2][M][F]
   double* tframe = nullptr;  // [2][M][Nb]
   double2* tspec = nullptr;  // [2][M][Nb]      target spectra (split call)

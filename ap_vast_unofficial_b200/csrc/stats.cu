@@ -77,23 +77,30 @@ __global__ void pack_stats_kernel(const double* __restrict__ S, double* __restri
 __global__ void __launch_bounds__(256, 1)
 syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, Dims D, int ntile, int SEG, int maxl,
                      unsigned path_mask, int m_first, int m_count, int comp, double* __restrict__ R,
-                     int* __restrict__ tile_cnt, int MA, int first) {
-  // blockIdx.z = microphone slice: the K dimension (microphones x P) is split per microphone and the per-microphone
-  // partial matrices are added up by a tree (syrk_reduce_kernel) -- a fixed-order accumulation over all M P terms
-  // would leave R with ~1e-14 relative rounding error, which the ill-conditioned pencil amplifies beyond the
-  // 1e-8 filter-parity bar at n = 4096.  Inside a microphone the DMMA accumulators only ever hold FLUSH_CHUNKS * KC
-  // terms: they are then added into a per-thread total kept in shared memory ([64][256] doubles, and with `comp` a
-  // float compensation term per entry that collects the rounding errors of those additions, TwoSum), so the
-  // sequential part of every sum is 256 terms long instead of P.
-  const int path = blockIdx.y;
+                     int* __restrict__ tile_cnt, int* __restrict__ slot_done, int nslots, int MA, int first) {
+  // grid (microphone slice, lower tile, path): the K dimension (microphones x P) is split per microphone and the
+  // per-microphone partial tiles are added up by a tree -- a fixed-order accumulation over all M P terms would leave R
+  // with ~1e-14 relative rounding error, which the ill-conditioned pencil amplifies beyond the 1e-8 filter-parity bar
+  // at n = 4096.  Inside a microphone the DMMA accumulators only ever hold FLUSH_CHUNKS * KC terms: they are then
+  // added into a per-thread total kept in shared memory ([64][256] doubles, and with `comp` a float compensation
+  // term per entry that collects the rounding errors of those additions, TwoSum), so the sequential part of every
+  // sum is 256 terms long instead of P.
+  // The microphone slice is the FASTEST grid index: the CTAs of one (tile, path) run at about the same time, their
+  // partial tiles go to one slot of a small ring (Pbuf: nslots x 16 tiles of 128 KB, L2-resident) and the CTA that
+  // finishes last sums them (below) while they are still in L2.
+  const int path = blockIdx.z;
   if (!((path_mask >> path) & 1u)) return;
-  const int mslice = blockIdx.z;
+  const int mslice = blockIdx.x;
   if (mslice >= m_count) return;
   // paths into zone A (0: A->A, 2: B->A) stop at the last real microphone of zone A (MA)
   const bool zoneA = (path & 1) == 0;
   if (zoneA && m_first + mslice >= MA) return;
+  const int tile = blockIdx.y;
+  // ring slot of this (tile, path): work items of the active paths in dispatch order
+  const int work = __popc(path_mask & ((1u << path) - 1u)) * ntile + tile;
+  const int slot = work % nslots, use = work / nslots;
   // decode linear lower-triangle tile index -> (bi, bj), bi >= bj
-  int t = blockIdx.x, bi = 0;
+  int t = tile, bi = 0;
   while (t >= bi + 1) { t -= bi + 1; ++bi; }
   const int bj = t;
   const int r0 = bi * TM, c0 = bj * TM;
@@ -194,7 +201,8 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
         for (int ct = 0; ct < 4; ++ct) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], b[ct]);
     }
     // (flushing the warps of an SM sub-partition in different chunks was measured and is slower: every chunk ends in a
-    // CTA barrier, so the chunk lasts as long as its slowest warp -- 70.3 instead of 64.1 ms per block at cfg-3)
+    // CTA barrier, so the chunk lasts as long as its slowest warp -- 70.3 instead of 64.1 ms per block at cfg-3; spreading
+    // the flush over the K loop, one row atom of 8 accumulators after every 8 k-steps, changes nothing: 58.9 vs 59.0 ms)
     if (comp >= 0 && ((it % FLUSH_CHUNKS) == FLUSH_CHUNKS - 1 || it == nit - 1)) {
       const bool first = !flushed;
       const bool last = it == nit - 1;
@@ -227,21 +235,31 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
     }
   }
 
-  // partial matrix of this microphone: lower triangle only (the reduction mirrors it)
-  double* Pp = Pbuf + ((size_t)mslice * 4 + path) * n * D.ldn;
+  // partial tile of this microphone -> its place in the ring slot ([slice][128][128]; the lower triangle matters).
+  // The slot was last used by the work item `nslots` places earlier in dispatch order: wait until its sum has been
+  // formed (in practice it was, several waves ago; the wait makes that a guarantee and cannot deadlock, because CTAs
+  // are dispatched in index order and the earlier work item depends on nothing later).
+  if (use > 0) {
+    if (tid == 0) {
+      int done;
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(slot_done + slot) : "memory");
+        if (done >= use) break;
+        __nanosleep(200);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  double* Pslot = Pbuf + (size_t)slot * SYRK_MAX_GROUP * TM * TM;
+  double* Pp = Pslot + (size_t)mslice * TM * TM;
 #pragma unroll
   for (int rt = 0; rt < 8; ++rt) {
-    const int r = r0 + wm + rt * 8 + gq;
-    if (r >= n) continue;
+    const int rl = wm + rt * 8 + gq;
 #pragma unroll
     for (int ct = 0; ct < 4; ++ct) {
-      const int c = c0 + wn + ct * 8 + 2 * tq;
-      if (c + 1 < n && (bi != bj || r >= c + 1)) {
-        *reinterpret_cast<double2*>(Pp + (size_t)r * D.ldn + c) = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
-      } else {
-        if (c < n && r >= c) Pp[(size_t)r * D.ldn + c] = acc[rt][ct][0];
-        if (c + 1 < n && r >= c + 1) Pp[(size_t)r * D.ldn + c + 1] = acc[rt][ct][1];
-      }
+      const int cl = wn + ct * 8 + 2 * tq;
+      *reinterpret_cast<double2*>(Pp + rl * TM + cl) = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
     }
   }
 
@@ -256,16 +274,15 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const int old = atomicAdd(&tile_cnt[path * ntile + blockIdx.x], 1);
+    const int old = atomicAdd(&tile_cnt[path * ntile + tile], 1);
     s_last = (old == contributors - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (tid == 0) tile_cnt[path * ntile + blockIdx.x] = 0;            // ready for the next launch
+  if (tid == 0) tile_cnt[path * ntile + tile] = 0;                  // ready for the next launch
   const bool mirror = zoneA ? (m_first + m_count >= MA) : (m_first + m_count >= D.M);
-  const size_t ps = (size_t)4 * n * D.ldn;                          // slice stride
-  const double* P0 = Pbuf + (size_t)path * n * D.ldn;
+  const size_t ps = (size_t)TM * TM;                                // slice stride inside the slot
   double* Rp = R + (size_t)path * n * D.ldn;
   // thread -> two consecutive columns of one row; 64 column pairs x 4 rows, two rows per thread and pass; all the
   // partial tiles of a pass are in flight together (the accumulators are dead: there is room for 2 x 16 pairs)
@@ -277,7 +294,7 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
     for (int u = 0; u < 2; ++u) {
       const int r = r0 + rb + rr + 4 * u, c = c0 + cp2;
       const bool ok = r < n && c <= r;        // (c is even and ldn is even: the pair stays inside the row)
-      const double* src = P0 + (size_t)r * D.ldn + c;
+      const double* src = Pslot + (size_t)(rb + rr + 4 * u) * TM + cp2;
 #pragma unroll
       for (int q = 0; q < SYRK_MAX_GROUP; ++q)
         v[u][q] = (ok && q < contributors) ? __ldcg(reinterpret_cast<const double2*>(src + (size_t)q * ps))
@@ -314,6 +331,12 @@ syrk_toeplitz_kernel(const double* __restrict__ Sp, double* __restrict__ Pbuf, D
         Rp[(size_t)r * D.ldn + c] = sum[u].x;
       }
     }
+  }
+  // the slot may be overwritten by the work item `nslots` places later
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(slot_done + slot), "r"(use + 1) : "memory");
   }
 }
 
@@ -605,12 +628,14 @@ int stage_stats(Handle& h) {
   // the multi-zone composition contribute nothing); groups of four microphones
   const int MA = (h.cfg.active_mics_A > 0 && h.cfg.active_mics_A < D.M) ? round_up(h.cfg.active_mics_A, 4) : D.M;
   const int G = h.syrk_group;
+  int* slot_done = h.syrk_cnt + 4 * ntile;
   for (int m0 = 0; m0 < D.M; m0 += G) {
     const int mc = std::min(G, D.M - m0);
     const unsigned mA = m0 < MA ? (pmask & 0x5u) : 0u, mB = pmask & 0xAu;
     if ((mA | mB) == 0u) continue;
-    syrk_toeplitz_kernel<<<dim3(ntile, 4, mc), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc, comp,
-                                                                h.R, h.syrk_cnt, MA, m0 == 0);
+    APV_CUDA_TRY(cudaMemsetAsync(slot_done, 0, (size_t)h.syrk_slots * sizeof(int), h.st));
+    syrk_toeplitz_kernel<<<dim3(mc, ntile, 4), 256, sm, h.st>>>(h.Sp, h.Pbuf, D, ntile, SEG, maxl, mA | mB, m0, mc, comp,
+                                                                h.R, h.syrk_cnt, slot_done, h.syrk_slots, MA, m0 == 0);
     ++nl;
   }
   APV_CUDA_TRY(cudaEventRecord(h.ev_syrk[1], h.st));

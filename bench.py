@@ -468,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
                 "share_of_step": kt_syrk / seq_ms if seq_ms > 0 else None,
                 "in_pipelined_region": {"kernel_ms_per_block": float(kt_pipe[1]), "achieved": ach_tf_pipe,
                                         "note": "shares the SMs with S5-S7 of the previous block"},
-                "traffic": prof.get("dram_bytes_per_block"), "traffic_per": "block (4 launches), like `achieved`",
+                "traffic": prof.get("dram_bytes_per_block"), "traffic_per": "block (one launch), like `achieved`",
                 "traffic_source": prof.get("source"),
                 "ncu_tensor_pipe_pct": prof.get("tensor_pipe_pct")}
     two_stage = n_panel < 0

@@ -20,6 +20,9 @@ shapes = [
     ("skinny Y = C22 V            (N=32, K=3072)", 3072, 32, 3072, 2, 0, 0, 0, 0, 0.0),
     ("square 4096^3 NT", 4096, 4096, 4096, 1, 1, 0, 0, 0, 0.0),
     ("square 4096^3 NN, 128x64 tile", 4096, 4096, 4096, 1, 0, 0, 0, 64, 0.0),
+    ("square 4096^3 NT, 128x64 tile", 4096, 4096, 4096, 1, 1, 0, 0, 64, 0.0),
+    ("K = 2048 NT (auto tile)", 4096, 4096, 2048, 2, 1, 0, 0, 0, 0.0),
+    ("K = 2048 NT, 128x64 tile", 4096, 4096, 2048, 2, 1, 0, 0, 64, 0.0),
 ]
 for name, M, N, K, batch, tb, tri, mir, bn, beta in shapes:
     ms = C.c_float(0)
