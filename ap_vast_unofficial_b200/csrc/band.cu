@@ -495,7 +495,14 @@ struct SbChase {
   long long* dbg;      // APV_TS_DEBUG: clock64 totals of CTA 0 (compute step / barrier wait; loader store / wait / load)
 };
 #define CH_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (lane == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
+// phases inside a step (compile with -DAPV_CHASE_FINE: the checks cost 1 ms of the kernel's 19.5 even when switched off)
+#ifdef APV_CHASE_FINE
 #define CH_FINE(k) do { if (fine) { const long long _t = clock64(); if (lane == 0) fine[k] += _t - tf; tf = _t; } } while (0)
+#define CH_FINE_START() do { if (fine) tf = clock64(); } while (0)
+#else
+#define CH_FINE(k)
+#define CH_FINE_START()
+#endif
 
 __device__ __forceinline__ int sweep_steps(int n, int s) { return (s <= n - 3) ? 1 + (n - s - 2) / NB2 : 0; }
 
@@ -532,8 +539,11 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   const int ngroups = (n - 2 + CGW - 1) / CGW;
   int* gprog = a.gprog + (size_t)z * ngroups;
   long long* dbgp = nullptr;
+#ifdef APV_CHASE_FINE
   long long* fine = nullptr;              // phases inside a step: B warp of sweep 0 -> dbg[20..27], its D warp -> dbg[28..31]
-  long long tk = clock64(), tf = tk;
+  long long tf = clock64();
+#endif
+  long long tk = clock64();
 
   // fetcher: rows [i0, i0 + 32) of the band -> window (zero rows beyond the matrix) once the previous group is past them
   auto load_chunk = [&](int g, int i0) {
@@ -582,7 +592,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
   for (int g = cta; g < ngroups; g += G) {
     // debug clocks: the first group only (it never waits for a predecessor: the unthrottled pace of one time step)
     dbgp = (a.dbg && blockIdx.x == 0 && g == 0 && (wib == 0 || role >= 2)) ? a.dbg + 8 + (role >= 2 ? 4 * (role - 1) : 0) : nullptr;
+#ifdef APV_CHASE_FINE
     fine = (a.dbg && blockIdx.x == 0 && g == 0 && wib < 2) ? a.dbg + (wib == 0 ? 20 : 28) : nullptr;
+#endif
     tk = clock64();
     const int s0 = g * CGW;
     const int nst0 = sweep_steps(n, s0);
@@ -604,7 +616,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) sb2st_chase_kernel(SbChase a) {
         if (k >= 0 && k < nst) {
           const int q0 = s + 1 + k * NB2;       // rows of the step (k = 0: the first diagonal block)
           double* line = lines[wib];
-          if (fine) tf = clock64();
+          CH_FINE_START();
           if (role == 0) {
             double* myrow = win_row(win, q0 + lane);
             if (k == 0) {
@@ -1199,7 +1211,9 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
       c.AB = AB; c.V2 = ws.Tm; c.gprog = prog; c.n = n; c.ldn = ldn; c.nz = nz; c.dbg = dbg.on ? dclk : nullptr;
       // groups in flight: a group lasts n / NB2 + 2 CGW time steps and the next one starts 2 CGW + 1 steps later
       const int ngroups = ceil_div(n - 2, CGW);
-      const int want = ceil_div(n / NB2 + 2 * CGW, 2 * CGW + 1) + 4;
+      // (measured at n = 4096: 20.6 ms from 18 CTAs per zone upwards, 20.7 with 16; every CTA more is an SM that the
+      // statistics of the next block cannot use in the multi-block path)
+      const int want = ceil_div(n / NB2 + 2 * CGW, 2 * CGW + 1);
       int G = std::max(1, std::min(std::min(sms / nz, want), ngroups));
       if (const char* e = getenv("APV_CHASE_G")) G = std::max(1, std::min(std::min(sms / nz, atoi(e)), ngroups));   // (experiment)
       const size_t smem = (size_t)CG_NSLOT * CG_PITCH * sizeof(double);
@@ -1231,8 +1245,10 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
             hc[0] * us, hc[1] * us, hc[2] * us, hc[3] * us, hc[4] * us, hc[5] * us, hc[6] * us);
     fprintf(stderr, "  chase us (first group): B-warp step %.0f | barrier %.0f ; storer: store+publish %.0f | barrier %.0f ; fetcher: wait %.0f | load %.0f | barrier %.0f\n",
             hc[8] * us, hc[11] * us, hc[12] * us, hc[15] * us, hc[17] * us, hc[18] * us, hc[19] * us);
+#ifdef APV_CHASE_FINE
     fprintf(stderr, "  chase B warp us (first group): load B %.1f | y = B v %.1f | house %.1f | pair sync %.1f | B -= y v^T %.1f | column sums %.1f | B -= v u^T %.1f | store %.1f ; D warp: load %.1f | wait for the reflector %.1f | two-sided %.1f | store %.1f\n",
             hc[20] * us, hc[21] * us, hc[22] * us, hc[23] * us, hc[24] * us, hc[25] * us, hc[26] * us, hc[27] * us, hc[28] * us, hc[29] * us, hc[30] * us, hc[31] * us);
+#endif
   }
   return OK;
 }
