@@ -240,6 +240,16 @@ __global__ void __launch_bounds__(256, 2) gemm_async_kernel(GemmArgs g) {
     if (s < nk) issue(s);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  if (g.beta != 0.0) {
+    // read-modify-write epilogue: the C tile is pulled into L2 while the K loop runs.  With 128 registers per thread the
+    // epilogue cannot keep all its loads in flight, so on a short K loop it paid several DRAM round trips one after the
+    // other (rank-64 band update at n = 4032: 0.155 ms with beta = 1 against 0.093 ms with beta = 0).
+    constexpr int LPR = BN / 16;                       // 128-byte lines per tile row
+    for (int i = tid; i < BM * LPR; i += 256) {
+      const int row = m0 + i / LPR, col = n0 + (i % LPR) * 16;
+      if (row < g.M && col < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)row * g.ldc + col));
+    }
+  }
   for (int kt = 0; kt < nk; ++kt) {
     asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
     __syncthreads();
