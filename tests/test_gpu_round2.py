@@ -270,3 +270,33 @@ def test_full_spectrum_path_at_cfg2_size(solver, monkeypatch):
     # the per-block filters (mu of the constructor) are the same prefix sums
     assert rel(eng.w_A[:, :, 0], eng.sweep([eng.mu])[0][0]) < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("env", [dict(APV_SYRK_SLOTS="2"), dict(APV_SYRK_GROUP="4"), dict(APV_SYRK_GROUP="8", APV_SYRK_SLOTS="3")])
+def test_syrk_ring_of_partial_tiles_is_bit_identical_whatever_its_size(env, monkeypatch):
+    """The statistics SYRK sums the per-microphone partial tiles in the CTA that finishes a tile last, out of a small ring
+    of slots (csrc/stats.cu).  The order of the sum is fixed by the code, so R must not depend on the ring size (2 slots:
+    nearly every CTA has to wait for its slot), nor on the number of microphones per launch as long as it is a multiple of the
+    tree width 4 (later launches accumulate into R), nor on the run: bitwise equal to the default."""
+    rA, rB, cfg, sA, sB, nblk, H = _case(L=8, J=64, K=128, Nb=512, N=640, V=16, M=9, nblk=4)   # n = 512: 10 tiles x 4 paths
+    apvast = _engine()
+
+    def run():
+        np.random.seed(5)
+        eng = apvast(rir_A=rA, rir_B=rB, device=0, **cfg)
+        for t in range(nblk):
+            eng.process_input_buffers(sA[t * H:(t + 1) * H], sB[t * H:(t + 1) * H])
+        out = [np.array(getattr(eng, k)) for k in ("R_A_to_A", "R_A_to_B", "R_B_to_A", "R_B_to_B", "w_A", "w_B")]
+        eng.close()
+        return out
+
+    ref = run()
+    again = run()
+    for a, b in zip(ref, again):
+        assert np.array_equal(a, b)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    assert np.allclose(ref[0], ref[0].T, rtol=0, atol=0)          # mirrored lower triangle
