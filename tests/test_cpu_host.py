@@ -152,3 +152,45 @@ def test_divide_and_conquer_prototype_against_lapack():
         assert np.max(np.abs(lam - ref)) <= 1e-13 * nrm
         assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-13
         assert np.max(np.abs(T @ Q - Q * lam[None, :])) <= 1e-13 * nrm
+
+
+def _run_bench(args, env_extra=None, launcher=None):
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    cmd = (launcher or [sys.executable]) + [os.path.join(root, "bench.py")] + args
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    return [json.loads(l) for l in lines]
+
+
+def test_bench_reference_arm_prints_one_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line, the arm's own metric /
+    unit / config, `impl`, a `cpu_baseline` describing the run and an `e2e` with zero copy bytes."""
+    lines = _run_bench(["--impl", "reference", "--workload", "small", "--steps", "2", "--warmup", "3"])
+    assert len(lines) == 1
+    d = lines[0]
+    assert d["impl"] == "reference" and d["metric"] == "filter_updates_per_sec" and d["unit"] == "updates/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("small")
+
+
+def test_bench_reference_arm_under_torchrun_rank0_alone_prints_and_keeps_its_blas_threads():
+    """Under torch.distributed.run (N > 1) rank 0 alone runs the arm and the other ranks exit 0 without work; the launcher
+    exports OMP_NUM_THREADS=1, which the arm must not inherit (that made it time out at N > 1 in round 1)."""
+    import os
+    import sys
+    launcher = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                "--master-addr", "127.0.0.1", "--master-port", "29541"]
+    lines = _run_bench(["--impl", "reference", "--gpus", "2", "--workload", "small", "--steps", "2", "--warmup", "3"],
+                       launcher=launcher)
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
+    if (os.cpu_count() or 1) > 1:
+        assert lines[0]["cpu_baseline"]["cores"] > 1
