@@ -300,3 +300,27 @@ def test_syrk_ring_of_partial_tiles_is_bit_identical_whatever_its_size(env, monk
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
     assert np.allclose(ref[0], ref[0].T, rtol=0, atol=0)          # mirrored lower triangle
+
+
+def test_bench_line_of_the_gpu_arm_carries_the_contract_keys():
+    """`python bench.py` (small workload, so that it takes seconds): ONE JSON line with the driver's keys -- metric / value /
+    e2e with host-copy bytes / gpu_launches / clocks -- and the tier's `roofline` and `cpu_baseline` objects."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "small", "--steps", "4", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "filter_updates_per_sec" and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["steps"] == 4
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["roofline"]["bound"] in ("hbm", "tensor") and 0 < d["roofline"]["frac"] < 1.5
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
