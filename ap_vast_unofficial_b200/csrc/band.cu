@@ -53,10 +53,52 @@ struct SbPanel {
   long long* dbg;      // APV_TS_DEBUG: clock64 totals per phase (rank 0 / warp 0 of zone 0)
 };
 
+
+// ---- distributed-shared-memory hand-over of the panel QR: remote stores that complete a transaction count on the
+// RECEIVER's mbarrier (st.async ... mbarrier::complete_tx), so a rank waits on its own barrier for exactly the bytes of
+// one column instead of the whole cluster meeting in a barrier.cluster per column
+__device__ __forceinline__ unsigned cl_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cl_mapa(const void* p, int rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cl_smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cl_st_async(unsigned remote_addr, double v, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cl_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cl_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CL_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni CL_WAIT_DONE;\n"
+      "bra.uni CL_WAIT_LOOP;\n"
+      "CL_WAIT_DONE:\n"
+      "}\n" ::"r"(cl_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 #define SB_TICK(k) do { if (dbgp) { const long long _t = clock64(); if (threadIdx.x == 0) dbgp[k] += _t - tk; tk = _t; } } while (0)
 
+// The slab of panel rows lives in REGISTERS: lane = panel column, warp w owns the local rows w, w + 32, .. (RPW of them,
+// x[t] = row w + 32 t).  A column step then needs two shuffles per row (the row's entry in column j, and after the
+// update its entry in column j + 1 for the next Gram row) and no shared-memory traffic at all; the shared-memory
+// version read and wrote every row once per column (7 shared-memory / shuffle wavefronts per row instead of 4, and
+// the load -> update -> store -> shuffle chain exposed to their latencies).  The slab goes to shared memory once, at
+// the end, to write V out transposed with coalesced stores.
+template <int RPW>
 __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
-  extern __shared__ __align__(16) double slab[];          // [rows_per][PP]
+  extern __shared__ __align__(16) double slab[];          // [rows_per][PP] (output staging only)
   __shared__ double xpart[2][QR_MAXCS][NB2];              // per-rank partial Gram rows (written by every rank)
   __shared__ double xrow[2][NB2];                         // the diagonal row of the current column (from its owner)
   __shared__ double red[QRW][NB2];
@@ -64,6 +106,7 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   __shared__ double taus[NB2];
   __shared__ double Tsm[NB2][PP];
   __shared__ double tqs[NB2], scal[2];                    // tau * (v^T P) per column, {1 / (alpha - beta), beta}
+  __shared__ __align__(8) unsigned long long colbar[2];   // per parity: the bytes of one column (partials of every rank + its diagonal row)
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int z = blockIdx.y, n = a.n, ldn = a.ldn, j0 = a.j0, r = j0 + NB2, npn = n - r;
@@ -72,32 +115,57 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
   long long* dbgp = (a.dbg && z == 0 && rank == 0) ? a.dbg : nullptr;
   long long tk = clock64();
   const int s0 = min(npn, rank * a.rows_per), s1 = min(npn, s0 + a.rows_per), nr = s1 - s0;   // slab rows [s0, s1)
-  for (int i = warp; i < nr; i += QRW) slab[i * PP + lane] = Cm[(size_t)(r + s0 + i) * ldn + j0 + lane];
-  cluster.sync();             // every CTA of the cluster runs before its shared memory is written remotely
+  if (threadIdx.x == 0) {
+    cl_mbar_init(&colbar[0], 1);
+    cl_mbar_init(&colbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  double x[RPW];
+#pragma unroll
+  for (int t = 0; t < RPW; ++t) {
+    const int i = warp + QRW * t;
+    x[t] = (i < nr) ? Cm[(size_t)(r + s0 + i) * ldn + j0 + lane] : 0.0;      // (rows beyond the slab hold zeros)
+  }
+  cluster.sync();             // every CTA of the cluster runs (and has initialised its barriers) before it is written remotely
   // partial Gram row of column 0 over the rows strictly below its diagonal
-  double acc = 0.0;
-  for (int i = warp; i < nr; i += QRW)
-    if (s0 + i > 0) acc = fma(slab[i * PP + lane], slab[i * PP], acc);
+  double acc;
+  {
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < RPW; ++t) {
+      const double x0 = __shfl_sync(0xffffffffu, x[t], 0);
+      if (s0 + warp + QRW * t > 0) a4[t & 3] = fma(x[t], x0, a4[t & 3]);
+    }
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
   SB_TICK(0);
+  const bool t0_special = s0 + warp <= NB2;       // (warp-uniform)
   for (int j = 0; j < NB2; ++j) {
     const int par = j & 1;
     red[warp][lane] = acc;
     __syncthreads();
     SB_TICK(1);
-    if (warp == 0) {           // one warp sums the CTA's partial Gram row and delivers it to every rank
+    // One column = one transaction phase of colbar[par]: every rank's partial Gram row (CS x 256 bytes) and, if the column
+    // has a diagonal row, that row from its owner (256 bytes).  The buffers of parity `par` are rewritten for column
+    // j + 2, which a rank sends only after it has received every rank's data of column j + 1 -- sent after those ranks
+    // had read column j: no barrier is needed to protect them.
+    if (warp == 0 && lane == 0)
+      cl_mbar_expect_tx(&colbar[par], (unsigned)((CS + (j < npn ? 1 : 0)) * NB2 * sizeof(double)));
+    if (warp < CS) {           // warp w sums the CTA's partial Gram row (redundantly, in parallel) and delivers it to rank w
       double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
       for (int w = 0; w < QRW; w += 4) {
         t0 += red[w][lane]; t1 += red[w + 1][lane]; t2 += red[w + 2][lane]; t3 += red[w + 3][lane];
       }
       const double t = (t0 + t1) + (t2 + t3);
-      for (int k = 0; k < CS; ++k) cluster.map_shared_rank(&xpart[par][rank][0], k)[lane] = t;
-    } else if (warp == 1 && j >= s0 && j < s1) {      // owner of the diagonal row broadcasts it
-      const double v = slab[(j - s0) * PP + lane];
-      for (int k = 0; k < CS; ++k) cluster.map_shared_rank(&xrow[par][0], k)[lane] = v;
+      cl_st_async(cl_mapa(&xpart[par][rank][lane], warp), t, cl_mapa(&colbar[par], warp));
     }
+    // the diagonal row j is the local row j - s0 < 32 of its owner: warp j - s0, register x[0]; that warp hands it to
+    // every rank
+    if (j >= s0 && j < s1 && warp == j - s0)
+      for (int k = 0; k < CS; ++k) cl_st_async(cl_mapa(&xrow[par][lane], k), x[0], cl_mapa(&colbar[par], k));
     SB_TICK(2);
-    cluster.sync();
+    if (warp == 0) cl_mbar_wait(&colbar[par], (unsigned)((j >> 1) & 1));
     SB_TICK(3);
     if (warp == 0) {           // reflector scalars once per CTA (32 warps doing this redundantly fill the FP64 pipe)
       double g0 = 0.0, g1 = 0.0;
@@ -111,9 +179,9 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       const double alpha = __shfl_sync(0xffffffffu, rowj, j), sigma = __shfl_sync(0xffffffffu, g, j);
       double beta = alpha, tau = 0.0, scale = 0.0;
       if (sigma > 0.0 && j < npn - 1) {      // (as warp_house below: one rsqrt and one reciprocal)
-        const double nrm2 = fma(alpha, alpha, sigma), r = rsqrt(nrm2);
-        beta = -copysign(nrm2 * r, alpha);
-        tau = fma(fabs(alpha), r, 1.0);
+        const double nrm2 = fma(alpha, alpha, sigma), rs = rsqrt(nrm2);
+        beta = -copysign(nrm2 * rs, alpha);
+        tau = fma(fabs(alpha), rs, 1.0);
         scale = 1.0 / (alpha - beta);
       }
       const double q = fma(scale, g, rowj);     // lane > j: (v^T P)[lane];  lane < j: (V^T V)[lane][j]
@@ -127,54 +195,53 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
     }
     __syncthreads();
     const double scale = scal[0], beta = scal[1], m1 = tqs[lane];
-    double a4[4] = {0.0, 0.0, 0.0, 0.0};
-    // rows of this warp: i = warp + QRW t; the rows gr = s0 + i <= j (leading rows of the first slabs) are finished
-    int i = warp;
-    if (s0 + i <= j) i += ((j - s0 - i) / QRW + 1) * QRW;
     const bool isj = lane == j;
-    if (i < nr && s0 + i == j + 1) {       // the next diagonal row takes the update but is not part of the next Gram row
-      const double vr = slab[i * PP + j] * scale, x = slab[i * PP + lane];
-      __syncwarp();
-      slab[i * PP + lane] = isj ? vr : fma(-vr, m1, x);
-      i += QRW;
+    // rows below the diagonal: x <- x - v_r m, v_r = x_j scale; column j keeps the reflector entry v_r itself, the lanes
+    // < j have m = 0.  Written per lane as x s - v_r m' with (s, m') = (scale, 0) in lane j and (1, m) elsewhere: no
+    // selects (the kernel is issue-bound: ncu, 57 % issue-active, 35 instructions per row in the branchy form).
+    const double sl = isj ? scale : 1.0, ml = isj ? 0.0 : m1;
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    // Only the first row of a warp can still be a finished row, the diagonal row or the next diagonal row (the rows
+    // w + 32 t, t >= 1, lie below row 32 of the panel): everything else takes the branch-free form.
+    if (t0_special) {
+      const int gr = s0 + warp;                       // global row of the panel (warp-uniform)
+      if (gr > j) {
+        const double vr = __shfl_sync(0xffffffffu, x[0], j) * scale;
+        x[0] = fma(-vr, ml, x[0] * sl);
+        if (gr > j + 1) {                             // (the next diagonal row takes the update but is not part of the next Gram row)
+          const double xb = __shfl_sync(0xffffffffu, x[0], (j + 1) & 31);
+          a4[0] = fma(x[0], xb, a4[0]);
+        }
+      } else if (gr == j) {                           // the diagonal row: R (v_j = 1 on it)
+        if (lane > j) x[0] -= m1;
+        else if (isj) x[0] = beta;
+      }
     }
-    for (; i < nr; i += 4 * QRW) {
-      double x[4], pj[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int ii = i + u * QRW;
-        const bool ok = ii < nr;
-        x[u] = ok ? slab[ii * PP + lane] : 0.0;
-        pj[u] = ok ? slab[ii * PP + j] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int ii = i + u * QRW;
-        const double vr = pj[u] * scale;
-        x[u] = isj ? vr : fma(-vr, m1, x[u]);       // column j keeps the reflector, the lanes < j have m1 = 0
-        if (ii < nr) slab[ii * PP + lane] = x[u];
-        const double xb = __shfl_sync(0xffffffffu, x[u], (j + 1) & 31);
-        a4[u] = fma(x[u], xb, a4[u]);                             // (rows beyond the slab hold zeros)
-      }
+    for (int t = 0; t < RPW; ++t) {
+      if (t == 0 && t0_special) continue;
+      const double vr = __shfl_sync(0xffffffffu, x[t], j) * scale;
+      x[t] = fma(-vr, ml, x[t] * sl);
+      const double xb = __shfl_sync(0xffffffffu, x[t], (j + 1) & 31);
+      a4[t & 3] = fma(x[t], xb, a4[t & 3]);
     }
     acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-    if (j >= s0 && j < s1 && warp == 0) {            // diagonal row: R
-      double x = slab[(j - s0) * PP + lane];
-      if (lane > j) x -= m1;                       // v_j = 1 on the diagonal row
-      else if (lane == j) x = beta;
-      slab[(j - s0) * PP + lane] = x;
-    }
-    // (the next iteration's barriers order these writes before any other warp reads them)
     SB_TICK(5);
   }
-  __syncthreads();
+  // the slab to shared memory for the outputs
+#pragma unroll
+  for (int t = 0; t < RPW; ++t) {
+    const int i = warp + QRW * t;
+    if (i < nr) slab[i * PP + lane] = x[t];
+  }
+  cluster.sync();              // (also the CTA barrier for the slab) nobody leaves while a remote store into its shared memory could still be under way
   // outputs: R (and zeros) into the panel of C, explicit V (row-major panel and as rows of VH)
   double* VP = a.VP + (size_t)z * n * NB2;
   for (int i = warp; i < nr; i += QRW) {
     const int gr = s0 + i;
-    const double x = slab[i * PP + lane];
-    Cm[(size_t)(r + gr) * ldn + j0 + lane] = (gr <= lane) ? x : 0.0;
-    VP[(size_t)(r + gr) * NB2 + lane] = (gr > lane) ? x : (gr == lane ? 1.0 : 0.0);
+    const double xv = slab[i * PP + lane];
+    Cm[(size_t)(r + gr) * ldn + j0 + lane] = (gr <= lane) ? xv : 0.0;
+    VP[(size_t)(r + gr) * NB2 + lane] = (gr > lane) ? xv : (gr == lane ? 1.0 : 0.0);
   }
   double* VH = a.VH + (size_t)z * n * ldn;
   for (int c = warp; c < NB2; c += QRW)
@@ -188,17 +255,17 @@ __global__ void __launch_bounds__(QRT, 1) sb_panel_qr_kernel(SbPanel a) {
       // T = (diag(1 / tau) + striu(V^T V))^-1 (the dlarft factor): lane = column c, back substitution
       //   t[c] = tau_c,  t[r] = -tau_r sum_{k = r+1 .. c} G[r][k] t[k]  (r < c),  zero below the diagonal
       double* Tp = a.Tp + (size_t)z * NB2 * NB2;
-      for (int r = NB2 - 1; r >= 0; --r) {
+      for (int rr = NB2 - 1; rr >= 0; --rr) {
         double a0 = 0.0, a1 = 0.0;
-        int k = r + 1;
+        int k = rr + 1;
         for (; k + 1 < NB2; k += 2) {
-          a0 = fma(Gs[r][k], Tsm[k][lane], a0);                  // (Tsm[k][lane] = 0 for k > lane)
-          a1 = fma(Gs[r][k + 1], Tsm[k + 1][lane], a1);
+          a0 = fma(Gs[rr][k], Tsm[k][lane], a0);                  // (Tsm[k][lane] = 0 for k > lane)
+          a1 = fma(Gs[rr][k + 1], Tsm[k + 1][lane], a1);
         }
-        if (k < NB2) a0 = fma(Gs[r][k], Tsm[k][lane], a0);
-        const double t = (r == lane) ? taus[r] : (r < lane ? -taus[r] * (a0 + a1) : 0.0);
-        Tsm[r][lane] = t;                                        // (column `lane` is private to this lane)
-        Tp[r * NB2 + lane] = t;
+        if (k < NB2) a0 = fma(Gs[rr][k], Tsm[k][lane], a0);
+        const double tt = (rr == lane) ? taus[rr] : (rr < lane ? -taus[rr] * (a0 + a1) : 0.0);
+        Tsm[rr][lane] = tt;                                        // (column `lane` is private to this lane)
+        Tp[rr * NB2 + lane] = tt;
       }
     }
   }
@@ -1082,11 +1149,14 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
   const bool lookahead = !dbg.on && ws.st2 != nullptr && !getenv("APV_TS_NO_LOOKAHEAD");
   auto launch_qr = [&](int j0, cudaStream_t qs) -> int {
     const int r = j0 + NB2, npn = n - r;
-    // cluster size: smallest of 1, 2, 4, 8, 16 whose slab fits in shared memory
-    const int max_rows = (184 * 1024) / (PP * (int)sizeof(double));
+    // cluster size: smallest of 1, 2, 4, 8, 16 whose slab fits in the registers of a CTA (16 rows per warp) and in its
+    // shared memory (output staging)
+    const int max_rows = std::min(16 * QRW, (184 * 1024) / (PP * (int)sizeof(double)));
     int CS = 1;
     while (CS < QR_MAXCS && ceil_div(npn, CS) > max_rows) CS *= 2;
     if (npn > 64) CS = std::max(CS, 8);                       // spread the rows anyway: the column loop is latency-bound
+    static const int cs16_from = getenv("APV_QR_CS16_FROM") ? atoi(getenv("APV_QR_CS16_FROM")) : 0;   // (experiment)
+    if (cs16_from > 0 && npn >= cs16_from) CS = std::max(CS, 16);
     if (ceil_div(npn, CS) > max_rows) {
       snprintf(g_err, sizeof(g_err), "two-stage tridiagonalisation: n = %d exceeds the panel capacity", n);
       return EINVAL_;
@@ -1097,10 +1167,13 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     const size_t smem = (size_t)p.rows_per * PP * sizeof(double);
     static PerDevice pd_configured; size_t& configured = pd_configured.cur();
     if (smem > configured) {
-      APV_CUDA_TRY(cudaFuncSetAttribute(sb_panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)std::max(smem, (size_t)(184 * 1024))));
-      APV_CUDA_TRY(cudaFuncSetAttribute(sb_panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = std::max(smem, (size_t)(184 * 1024));
+      const int want = (int)std::max(smem, (size_t)(184 * 1024));
+      for (const void* f : {(const void*)sb_panel_qr_kernel<2>, (const void*)sb_panel_qr_kernel<4>,
+                            (const void*)sb_panel_qr_kernel<8>, (const void*)sb_panel_qr_kernel<16>}) {
+        APV_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        APV_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      }
+      configured = (size_t)want;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, nz); cfg.blockDim = dim3(QRT); cfg.dynamicSmemBytes = smem; cfg.stream = qs;
@@ -1109,7 +1182,16 @@ int twostage_run(JdiagWs& ws, cudaStream_t st, int* launches) {
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     dbg.begin(qs);
-    APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel, p));
+    // rows per warp held in registers: the smallest instantiation that covers the slab
+    const int rpw = ceil_div(p.rows_per, QRW);
+    if (rpw > 16) {
+      snprintf(g_err, sizeof(g_err), "two-stage tridiagonalisation: n = %d exceeds the panel capacity", n);
+      return EINVAL_;
+    }
+    if (rpw <= 2) APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel<2>, p));
+    else if (rpw <= 4) APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel<4>, p));
+    else if (rpw <= 8) APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel<8>, p));
+    else APV_CUDA_TRY(cudaLaunchKernelEx(&cfg, sb_panel_qr_kernel<16>, p));
     dbg.end(qs, 0);
     ++*launches;
     return OK;
