@@ -4,10 +4,11 @@
 // Here the O(n^3) work is all BLAS-3 on the FP64 tensor cores and the BLAS-2 part runs on a band that stays in L2:
 //
 //   stage 1 (dense -> band, half bandwidth NB2 = 32), per panel of NB2 columns
-//     sb_panel_qr_kernel   Householder QR of the sub-diagonal panel  C[r:, j0:j0+NB2]  (r = j0 + NB2) held in the
-//                          DISTRIBUTED shared memory of one thread-block cluster per zone: one DSMEM exchange and one
-//                          cluster barrier per column (a Gram row of the column gives norm, reflector, the row
-//                          v^T P and the column of V^T V needed by the compact-WY factor T in the same reduction)
+//     sb_panel_qr_kernel   Householder QR of the sub-diagonal panel  C[r:, j0:j0+NB2]  (r = j0 + NB2) spread over one
+//                          thread-block cluster per zone, the rows in registers: per column one exchange through
+//                          distributed shared memory (st.async into the receiver's transaction barrier, no cluster
+//                          barrier); a Gram row of the column gives norm, reflector, the row v^T P and the column of
+//                          V^T V needed by the compact-WY factor T in the same reduction
 //     gemm (split-K)       Y = C22 V                                       (DMMA, skinny tile)
 //     sb_w1/w2_kernel      X = Y T,  W = X - 1/2 V T^T (V^T X),  panels Z1 = [V | W], Z2 = [W | V]
 //     gemm                 C22 -= Z1 Z2^T   (= V W^T + W V^T)              (DMMA)
