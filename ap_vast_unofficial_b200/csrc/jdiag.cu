@@ -392,6 +392,20 @@ __global__ void mirror_lower_kernel(double* __restrict__ C, int n, int ldn) {
 // per eigenvalue, grid (V / 8, nz)) for full-spectrum requests where throughput matters.  256 threads; smem 2n doubles.
 constexpr int BIS_T = 256;
 
+// 1 / t to about one ulp: the 20-bit seed of the special-function unit and two Newton steps (four dependent FMAs).  The
+// correctly rounded __drcp_rn costs ~40 cycles more per step of the recurrence below, which is a chain of n dependent
+// reciprocals per shift (ncu: eig_bisect_kernel 23 instructions and ~137 cycles per step, 2 warps per SM sub-partition);
+// the count is insensitive to the last ulp of t.  |t| >= pivmin >= DBL_MIN, so the seed neither overflows nor sees a
+// subnormal; a subnormal result (|t| > 4.5e307) is flushed to zero, which is the right limit of e^2 / t.
+__device__ __forceinline__ double rcp_fast(double t) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+  double e = fma(-t, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-t, y, 1.0);
+  return fma(y, e, y);
+}
+
 __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n,
                                            double x, double pivmin) {
   double t = d[0] - x;
@@ -399,7 +413,7 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   int c = (t <= 0.0);
 #pragma unroll 4
   for (int i = 1; i < n; ++i) {
-    t = fma(-e2[i - 1], __drcp_rn(t), d[i] - x);
+    t = fma(-e2[i - 1], rcp_fast(t), d[i] - x);
     if (fabs(t) < pivmin) t = -pivmin;
     c += (t <= 0.0);
   }
