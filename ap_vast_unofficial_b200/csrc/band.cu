@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(Q2T) sb2st_apply_q2_kernel(double* __restrict_
 // the higher sweeps come first); finished rows travel between chains through global memory with release /
 // acquire block counters, like the rows of the bulge chasing.  The reflectors of a block (32 x 32 doubles) are
 // staged in shared memory and read as broadcasts.  Cooperative launch, 128 threads, one chain per warp.
-constexpr int Q2W_T = 128;
+constexpr int Q2W_T = 256;        // (8 chains per CTA: the same chains in flight on half as many SMs as with 4)
 constexpr int Q2W_MAXV = 8192;
 
 struct SbQ2 {
@@ -859,7 +859,8 @@ struct SbQ2 {
 };
 
 __global__ void __launch_bounds__(Q2W_T, 1) sb2st_apply_q2_wave_kernel(SbQ2 a) {
-  __shared__ __align__(16) double vs_all[Q2W_T / 32][32][34];
+  extern __shared__ __align__(16) double q2w_sm[];                 // [Q2W_T / 32][32][34]
+  double (*vs_all)[32][34] = reinterpret_cast<double (*)[32][34]>(q2w_sm);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = a.n, ldn = a.ldn, Vp = a.Vp;
   const int nprob = a.nz * a.nhalf;
@@ -1369,7 +1370,13 @@ int twostage_apply_q2(JdiagWs& ws, cudaStream_t st, int* launches) {
     const int warps = std::min(nprob * q.ngrp, sms * (Q2W_T / 32) / nprob * nprob);
     const int grid = std::max(1, ceil_div(std::max(warps, nprob), Q2W_T / 32));
     void* args[] = {(void*)&q};
-    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb2st_apply_q2_wave_kernel, dim3(grid), dim3(Q2W_T), args, 0, st));
+    const size_t wsm = (size_t)(Q2W_T / 32) * 32 * 34 * sizeof(double);
+    static PerDevice pd_wcfg; size_t& wcfg = pd_wcfg.cur();
+    if (!wcfg) {
+      APV_CUDA_TRY(cudaFuncSetAttribute(sb2st_apply_q2_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+      wcfg = 1;
+    }
+    APV_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)sb2st_apply_q2_wave_kernel, dim3(grid), dim3(Q2W_T), args, wsm, st));
   } else {
     sb2st_apply_q2_kernel<<<dim3(ws.V, ws.nz), Q2T, smem, st>>>(ws.iv, ws.Tm, n, ws.ldn, ws.Vp);
   }
