@@ -517,10 +517,12 @@ int apv_create(const apv_config* cfg, const double* rir_A, const double* rir_B, 
   if (h->nz == 1) h->zones[1] = h->zones[0];
   if (h->nz > 0) TRYB(jdiag_alloc(h->jd, D.n, D.V, h->nz, cfg->eig_mode));
   {
-    // joint diagonalisations in flight in multi-block calls: 2 where one of them nearly fills the chip (measured at
-    // cfg-3: 110.5 -> 99.2 ms per block), 4 below n = 2048 where S5 is latency-bound throughout; APV_DEPTH overrides
+    // joint diagonalisations in flight in multi-block calls: 3 from n = 2048 (measured at cfg-3: one 110.5, two 97.4,
+    // three 94.5, four 94.4 ms per block -- with the latency-bound kernels of S5 on fewer SMs since the second session
+    // of round 2 a third one pays; in the first session it did not: 99.2 vs 97.6), 4 below n = 2048 where S5 is
+    // latency-bound throughout; APV_DEPTH overrides
     const char* de = getenv("APV_DEPTH");
-    TRYB(ensure_depth(*h, de ? atoi(de) : (D.n < 2048 ? 4 : 2)));
+    TRYB(ensure_depth(*h, de ? atoi(de) : (D.n < 2048 ? 4 : 3)));
   }
   if (fft_plan(D.Nb, h->rad, &h->nrad) != OK) return bail(fail(EINVAL_, "cannot factor block size %d", D.Nb));
 
