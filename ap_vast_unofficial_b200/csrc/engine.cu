@@ -394,7 +394,7 @@ int ensure_ring(Handle& h, int cap) {
 extern "C" {
 
 const char* apv_last_error(void) { return apv::g_err; }
-const char* apv_version(void) { return "apvast_b200 0.2 (sm_100a)"; }
+const char* apv_version(void) { return "apvast_b200 0.3 (sm_100a)"; }
 
 size_t apv_tensor_size(const apv_handle* h, int id) {
   if (!h) return 0;
